@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: batched PDQ hashing throughput
+(BASELINE.json configs[1]: 1024x768 RGB8 images) plus, reported in the same JSON line, the
+all-pairs Hamming grouping of 500k hashes (configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU path on the host cores
+
+A "step" is one pass of the hashing hot path over one batch of `--batch` synthetic images.
+`value` is device-resident throughput (inputs in HBM before the timed region); `e2e` is the same
+metric through the public API with pinned HOST buffers (H2D of the pixels and D2H of the hashes
+inside the timed region).  One process per GPU; for N > 1 launch under torchrun.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W, IMG_C = 768, 1024, 3            # BASELINE.json configs[1]
+ALGO_BYTES_PER_IMAGE = IMG_H * IMG_W * IMG_C + 36   # pixels read + 32 B hash + 4 B quality
+HAMMING_N = 500_000                            # BASELINE.json configs[2]
+HAMMING_T = 31
+POPC_PER_PAIR = 8                              # algorithmic POPC.32 per 256-bit pair
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per step (device-resident arm)")
+    ap.add_argument("--e2e-batch", type=int, default=1024, help="images per step (pinned-host arm)")
+    ap.add_argument("--host-pool", type=int, default=256, help="distinct images in the pinned host pool")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--hamming-n", type=int, default=HAMMING_N)
+    ap.add_argument("--skip-hamming", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-peaks", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_pool_device(torch, count, seed):
+    """(count, 768, 1024, 3) uint8 on the current device: blocky low-frequency field + pixel noise
+    + per-channel offset, generated in slabs to bound scratch."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((count, IMG_H, IMG_W, IMG_C), dtype=torch.uint8, device=dev)
+    ys = (torch.arange(IMG_H, device=dev) * 24 // IMG_H)
+    xs = (torch.arange(IMG_W, device=dev) * 32 // IMG_W)
+    slab = 32
+    for s in range(0, count, slab):
+        m = min(slab, count - s)
+        field = torch.randn((m, 24, 32), generator=g, device=dev) * 50.0
+        base = field[:, ys][:, :, xs].unsqueeze(-1)
+        noise = torch.randn((m, IMG_H, IMG_W, IMG_C), generator=g, device=dev) * 20.0
+        offs = torch.randn((m, 1, 1, IMG_C), generator=g, device=dev) * 10.0
+        out[s:s + m] = (base + noise + offs + 128.0).clamp_(0, 255).to(torch.uint8)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be
+    built here) on all host threads, same metric / config; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from rupphash_b200.synth import synth_images
+    oracle.build()
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 4, 64)
+    imgs = synth_images(per_step, IMG_H, IMG_W, seed=0xB200)
+    for _ in range(args.warmup):
+        oracle.pdq_batch(imgs[: max(cores, 8)], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.pdq_batch(imgs, threads=cores)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "pdq_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched PDQ hashing of 1024x768 RGB8 images (CPU oracle port of "
+                               "pdqhash.rs, one image per task over all host threads)",
+                   "images_per_step": per_step, "image": [IMG_H, IMG_W, IMG_C]},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} images/step x {args.steps} steps"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rupphash_b200 import _lib, pdqhash, scanner
+    from rupphash_b200.synth import planted_hashes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; rupphash_b200 has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    # a dedicated non-default stream shared by torch, NCCL and the library, so that the CUDA
+    # events below are recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_gbs, peak_src = peaks()
+    B, K, W = args.batch, args.steps, args.warmup
+
+    # ------------------------------------------------------------- PDQ, device resident ----
+    pool = synth_pool_device(torch, B, seed=0xB200 + rank)        # B x 2.36 MB >> 126 MB L2
+    out_hash = torch.empty((B, 32), dtype=torch.uint8, device="cuda")
+    out_q = torch.empty((B,), dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+
+    def step_device():
+        ctx.check(L.rh_pdq_hash_batch(ctx.handle, pool.data_ptr(), _lib.LAYOUT_RGB8, B, IMG_W, IMG_H, 0, 0,
+                                      out_hash.data_ptr(), out_q.data_ptr(), None, None, None))
+
+    for _ in range(W):
+        step_device()
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = 0.0
+    ev0.record(stream)
+    for _ in range(K):
+        step_device()
+        kernel_ms += ctx.last_kernel_time()[0]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / K
+    value = world * B * K / (ms_total * 1e-3)
+    kernel_ms_per_step = max_over_ranks(kernel_ms / K)
+    achieved_gbs = B * ALGO_BYTES_PER_IMAGE / (kernel_ms_per_step * 1e-3) / 1e9
+
+    # ------------------------------------------------------------- PDQ, end to end ---------
+    Be = min(args.e2e_batch, B)
+    hp = min(args.host_pool, Be)
+    host_pool = torch.empty((Be, IMG_H, IMG_W, IMG_C), dtype=torch.uint8, pin_memory=True)
+    for s in range(0, Be, hp):
+        m = min(hp, Be - s)
+        host_pool[s:s + m].copy_(pool[:m])
+    torch.cuda.synchronize()
+    host_np = host_pool.numpy()
+    e2e_steps = max(2, min(K, 5))
+    pdqhash.hash_batch(host_np, ctx=ctx)      # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        res = pdqhash.hash_batch(host_np, ctx=ctx)   # H2D pixels + kernels + D2H hash/quality/valid
+    ev1.record(stream)
+    barrier()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * Be * e2e_steps / e2e_wall
+    h2d_bytes = Be * IMG_H * IMG_W * IMG_C
+    d2h_bytes = Be * (32 + 4 + 1)
+    same = bool(np.array_equal(res["hash"], out_hash[:Be].cpu().numpy()))
+
+    line = {
+        "metric": "pdq_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched PDQ hashing of synthetic 1024x768 RGB8 images, "
+                               "device-resident pool cycled per step",
+                   "images_per_step_per_gpu": B, "image": [IMG_H, IMG_W, IMG_C],
+                   "l2_policy": f"inputs larger than L2: {B * IMG_H * IMG_W * IMG_C / 1e9:.2f} GB read per step",
+                   "parallelism": f"independent batches per GPU x{world} (no collective)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "images_per_step_per_gpu": Be, "steps": e2e_steps,
+                "matches_device_resident_hashes": same},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_step": kernel_ms_per_step,
+                     "algorithmic_bytes_per_image": ALGO_BYTES_PER_IMAGE},
+    }
+
+    # ------------------------------------------------------------- integer / copy peaks -----
+    pk = None
+    if not args.skip_peaks and rank == 0:
+        pk = ctx.measure_peaks()
+        line["measured_peaks"] = pk
+        if pk["h2d_gbs"] > 0:
+            line["e2e"]["h2d_roofline_frac"] = (e2e_value / world) * IMG_H * IMG_W * IMG_C / 1e9 / pk["h2d_gbs"]
+
+    # ------------------------------------------------------------- Hamming grouping --------
+    if not args.skip_hamming:
+        n = args.hamming_n
+        hashes, low_conf = planted_hashes(n, seed=0xB200, n_clusters=5000, identical_block=1000,
+                                          threshold=HAMMING_T)
+        d_hashes = torch.from_numpy(hashes).cuda()
+        d_lc = torch.from_numpy(low_conf).cuda()
+        pairs = n * (n - 1) // 2
+
+        def group_device():
+            if world == 1:
+                labels, cnt = scanner.group_labels(d_hashes, HAMMING_T, low_conf=d_lc, ctx=ctx)
+                return labels, cnt, ctx.last_kernel_time()[0]
+            parent, cnt = scanner.group_shard(d_hashes, HAMMING_T, rank, world, low_conf=d_lc, ctx=ctx)
+            kms = ctx.last_kernel_time()[0]
+            gathered = torch.empty((world, n), dtype=parent.dtype, device="cuda")
+            dist.all_gather_into_tensor(gathered, parent)
+            total = torch.tensor([cnt], dtype=torch.int64, device="cuda")
+            dist.all_reduce(total)
+            labels = scanner.merge_forests(gathered, ctx)
+            return labels, int(total.item()), kms
+
+        group_device()
+        barrier()
+        reps = 3
+        kms_sum = 0.0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            labels, edges, kms = group_device()
+            kms_sum += kms
+        barrier()
+        wall_dev = max_over_ranks((time.perf_counter() - t0) / reps)
+        tile_ms = max_over_ranks(kms_sum / reps)
+        # end to end: hashes in pinned host memory -> labels in host memory
+        h_hashes = torch.from_numpy(hashes).pin_memory()
+        h_lc = torch.from_numpy(low_conf).pin_memory()
+        h_labels = torch.empty(n, dtype=torch.int32).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        d_hashes.copy_(h_hashes, non_blocking=True)
+        d_lc.copy_(h_lc, non_blocking=True)
+        labels, edges2, _ = group_device()
+        h_labels.copy_(labels if torch.is_tensor(labels) else torch.from_numpy(np.asarray(labels).view(np.int32)))
+        barrier()
+        wall_e2e = max_over_ranks(time.perf_counter() - t0)
+        ham = {"metric": "hamming_pairs_per_sec", "n_hashes": n, "threshold": HAMMING_T, "pairs": pairs,
+               "value": pairs / wall_dev, "unit": "pairs/s", "tile_kernel_ms": tile_ms,
+               "tile_kernel_pairs_per_s": pairs / (tile_ms * 1e-3) if tile_ms > 0 else None,
+               "group_wall_ms_device_resident": wall_dev * 1e3, "group_wall_ms_e2e_pinned_host": wall_e2e * 1e3,
+               "edges": int(edges), "edges_e2e": int(edges2), "groups": None, "n_gpus": world,
+               "exchange": "none (1 GPU)" if world == 1 else "NCCL all-gather of n x u32 forests + all-reduce of edge counts"}
+        if pk:
+            peak_pairs = pk["popc_per_s"] / POPC_PER_PAIR
+            per_gpu = pairs / world / (tile_ms * 1e-3)
+            ham["roofline"] = {"bound": "int-pipe (POPC.32)", "achieved": per_gpu * POPC_PER_PAIR,
+                               "peak": pk["popc_per_s"], "unit": "POPC/s", "frac": per_gpu / peak_pairs,
+                               "note": "algorithmic 8 POPC per pair over the measured POPC issue rate; the kernel "
+                                       "executes 4 POPC + 16 LOP3 per pair (carry-save), so frac may exceed 1",
+                               "lop3_frac": per_gpu * 16 / pk["lop3_per_s"]}
+        line["hamming"] = ham
+
+    # ------------------------------------------------------------- CPU baseline (rank 0) ---
+    if rank == 0 and not args.skip_cpu:
+        import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        ns = args.cpu_sample or max(2 * cores, min(1024, Be))
+        ns = min(ns, Be)
+        t0 = time.perf_counter()
+        ref = oracle.pdq_batch(host_np[:ns], threads=cores)
+        dt = time.perf_counter() - t0
+        ident = int((ref["hash"] == res["hash"][:ns]).all(axis=1).sum())
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} images of the step's batch, oracle/ (C port of pdqhash.rs), "
+                                          f"{cores} threads, {dt:.2f} s",
+                                "parity_identical_hashes": ident, "parity_checked": ns}
+        if not args.skip_hamming:
+            t0 = time.perf_counter()
+            ref_labels, ref_cnt, _ = oracle.group_generic(hashes, HAMMING_T, low_conf=low_conf, threads=cores)
+            dt = time.perf_counter() - t0
+            lab = labels.cpu().numpy().view(np.uint32) if torch.is_tensor(labels) else np.asarray(labels)
+            line["hamming"]["cpu_baseline"] = {
+                "group_wall_ms": dt * 1e3, "pairs_equivalent_per_s": pairs / dt, "cores": cores, "kind": "port",
+                "sample": f"full {n} hashes, oracle MIH probing + sequential union-find (scanner.rs:1673-1807)",
+                "labels_identical": bool(np.array_equal(lab, ref_labels)), "edges_identical": bool(ref_cnt == edges)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

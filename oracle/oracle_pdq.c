@@ -13,6 +13,28 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Per-thread scratch planes, grown on demand and reused across images -- the analogue of the
+ * reference's thread-local Resizer (pdqhash.rs:38-42).  Without it every image mmaps and
+ * unmaps ~3 MB and the page-fault / TLB-shootdown traffic serialises the worker threads. */
+enum { SCR_LUMA = 0, SCR_RESIZED, SCR_RTMP, SCR_PLANE, SCR_JTMP, SCR_COUNT };
+static __thread void *t_scr[SCR_COUNT];
+static __thread size_t t_scr_bytes[SCR_COUNT];
+static void *scratch(int slot, size_t bytes) {
+    if (t_scr_bytes[slot] < bytes) {
+        free(t_scr[slot]);
+        t_scr[slot] = malloc(bytes);
+        t_scr_bytes[slot] = t_scr[slot] ? bytes : 0;
+    }
+    return t_scr[slot];
+}
+static void scratch_release(void) {
+    for (int i = 0; i < SCR_COUNT; i++) {
+        free(t_scr[i]);
+        t_scr[i] = NULL;
+        t_scr_bytes[i] = 0;
+    }
+}
+
 #define MIN_HASHABLE_DIM 5u   /* pdqhash.rs:17 */
 #define JAROSZ_PASSES 2       /* pdqhash.rs:18 */
 #define DOWNSAMPLE_DIMS 512u  /* pdqhash.rs:19 */
@@ -141,7 +163,7 @@ int orc_resize_box_u8(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, 
     box_coeffs bx, by;
     if (box_precompute(sw, dw, &bx)) return -1;
     if (box_precompute(sh, dh, &by)) return -1;
-    uint8_t *tmp = (uint8_t *)malloc((size_t)dw * sh);
+    uint8_t *tmp = (uint8_t *)scratch(SCR_RTMP, (size_t)dw * sh);
     if (!tmp) return -1;
     for (int y = 0; y < sh; y++) {
         const uint8_t *row = src + (size_t)y * sw;
@@ -160,7 +182,6 @@ int orc_resize_box_u8(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, 
             dst[(size_t)o * dw + x] = clip8(acc, by.precision);
         }
     }
-    free(tmp);
     box_free(&bx);
     box_free(&by);
     return 0;
@@ -213,12 +234,11 @@ void orc_box_one_d(const float *in, size_t in_start, float *out, size_t out_star
 
 /* pdqhash.rs:398-426 */
 void orc_jarosz(float *buf, size_t rows, size_t cols, size_t w_rows, size_t w_cols, size_t nreps) {
-    float *tmp = (float *)calloc(rows * cols, sizeof(float));
+    float *tmp = (float *)scratch(SCR_JTMP, rows * cols * sizeof(float));
     for (size_t rep = 0; rep < nreps; rep++) {
         for (size_t i = 0; i < rows; i++) orc_box_one_d(buf, i * cols, tmp, i * cols, cols, 1, w_rows);
         for (size_t j = 0; j < cols; j++) orc_box_one_d(tmp, j, buf, j, rows, cols, w_cols);
     }
-    free(tmp);
 }
 
 /* pdqhash.rs:428-443 */
@@ -388,14 +408,13 @@ void orc_dihedral(const float *c, uint8_t *out) {
 void orc_pdq_from_luma(const uint8_t *luma, uint32_t w, uint32_t h, float *coeffs, float *quality,
                        float *buf64_out) {
     size_t cols = w, rows = h;
-    float *plane = (float *)malloc(rows * cols * sizeof(float));
+    float *plane = (float *)scratch(SCR_PLANE, rows * cols * sizeof(float));
     for (size_t i = 0; i < rows * cols; i++) plane[i] = (float)luma[i]; /* :244 */
     size_t w_rows = (cols + BUF - 1) / BUF;                               /* :246 */
     size_t w_cols = (rows + BUF - 1) / BUF;                               /* :247 */
     orc_jarosz(plane, rows, cols, w_rows, w_cols, JAROSZ_PASSES);
     float buf64[BUF * BUF];
     orc_decimate64(plane, rows, cols, buf64);
-    free(plane);
     *quality = orc_quality(buf64, BUF, BUF);
     orc_dct64_to_16(buf64, coeffs);
     if (buf64_out) memcpy(buf64_out, buf64, sizeof(buf64));
@@ -409,7 +428,7 @@ int orc_pdq_features(const uint8_t *px, int layout, uint32_t w, uint32_t h, floa
     uint8_t *luma_owned = NULL;
     const uint8_t *luma = px;
     if (layout != ORC_LAYOUT_LUMA8) { /* :172-175 */
-        luma_owned = (uint8_t *)malloc(n);
+        luma_owned = (uint8_t *)scratch(SCR_LUMA, n);
         orc_luma601(px, layout, n, luma_owned);
         luma = luma_owned;
     }
@@ -418,7 +437,7 @@ int orc_pdq_features(const uint8_t *px, int layout, uint32_t w, uint32_t h, floa
     if (w > DOWNSAMPLE_DIMS || h > DOWNSAMPLE_DIMS) { /* :181-188 */
         uint32_t nw, nh;
         orc_target_dimensions(w, h, DOWNSAMPLE_DIMS, &nw, &nh);
-        resized = (uint8_t *)malloc((size_t)nw * nh);
+        resized = (uint8_t *)scratch(SCR_RESIZED, (size_t)nw * nh);
         if (orc_resize_box_u8(luma, (int)w, (int)h, resized, (int)nw, (int)nh) == 0) {
             luma = resized;
             pw = nw;
@@ -426,8 +445,6 @@ int orc_pdq_features(const uint8_t *px, int layout, uint32_t w, uint32_t h, floa
         } /* else: hash at full resolution */
     }
     orc_pdq_from_luma(luma, pw, ph, coeffs, quality, buf64);
-    free(resized);
-    free(luma_owned);
     return 0;
 }
 
@@ -476,6 +493,7 @@ static void *batch_worker(void *arg) {
         if (job->out_quality) job->out_quality[i] = q;
         if (job->out_coeffs) memcpy(job->out_coeffs + i * 256, coeffs, sizeof(coeffs));
     }
+    scratch_release(); /* worker threads live for one batch */
     return NULL;
 }
 

@@ -1,0 +1,184 @@
+// common.cuh -- context, error plumbing and buffer staging shared by every translation unit
+// of librupphash_b200.so.  Nothing here depends on PyTorch; the library is plain CUDA C++.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rupphash_b200.h"
+
+struct rh_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;   // compute stream owned by the ctx
+    cudaStream_t stream = nullptr;       // stream in use (own_stream or the caller's)
+    cudaStream_t copy_stream = nullptr;  // H2D staging stream of the batching pipeline
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+    double last_ms = 0.0, last_units = 0.0;
+    int sm_count = 148;
+    // growable device scratch, one buffer per slot
+    static constexpr int kSlots = 24;
+    void *slot_ptr[kSlots] = {};
+    size_t slot_bytes[kSlots] = {};
+    // growable pinned host scratch
+    static constexpr int kHostSlots = 4;
+    void *hslot_ptr[kHostSlots] = {};
+    size_t hslot_bytes[kHostSlots] = {};
+    bool dct_ready = false;
+};
+
+namespace rh {
+
+enum Slot {
+    S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_IN4,   // staged inputs
+    S_OUT0, S_OUT1, S_OUT2, S_OUT3, S_OUT4,  // staged outputs
+    S_W0, S_W1, S_W2, S_W3, S_W4, S_W5, S_W6, S_W7, S_W8, S_W9, S_W10, S_W11, S_W12, S_W13  // work
+};
+
+inline int fail(rh_ctx *ctx, int code, const char *what, cudaError_t ce = cudaSuccess) {
+    if (ctx) {
+        char buf[512];
+        if (ce != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+#define RH_CUDA(ctx, call)                                                        \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return rh::fail((ctx), RH_ECUDA, #call, _e);       \
+    } while (0)
+
+#define RH_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != RH_OK) return _s;   \
+    } while (0)
+
+// Launch check: counts the launch and turns a launch failure into RH_ECUDA.
+#define RH_LAUNCHED(ctx, name)                                                    \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) return rh::fail((ctx), RH_ECUDA, "launch " name, _e); \
+    } while (0)
+
+inline int scratch(rh_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_bytes[slot] < bytes) {
+        if (ctx->slot_ptr[slot]) {
+            // the buffer may still be in use by queued work
+            RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            cudaFree(ctx->slot_ptr[slot]);
+            ctx->slot_ptr[slot] = nullptr;
+            ctx->slot_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        want = (want + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&ctx->slot_ptr[slot], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, RH_ENOMEM, "cudaMalloc scratch", e);
+        }
+        ctx->slot_bytes[slot] = want;
+    }
+    *out = ctx->slot_ptr[slot];
+    return RH_OK;
+}
+
+inline int host_scratch(rh_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->hslot_bytes[slot] < bytes) {
+        if (ctx->hslot_ptr[slot]) {
+            RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            cudaFreeHost(ctx->hslot_ptr[slot]);
+            ctx->hslot_ptr[slot] = nullptr;
+            ctx->hslot_bytes[slot] = 0;
+        }
+        cudaError_t e = cudaMallocHost(&ctx->hslot_ptr[slot], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, RH_ENOMEM, "cudaMallocHost scratch", e);
+        }
+        ctx->hslot_bytes[slot] = bytes;
+    }
+    *out = ctx->hslot_ptr[slot];
+    return RH_OK;
+}
+
+// true when p is device-accessible memory of some CUDA device (device or managed)
+inline bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input staging: a device pointer is used in place, a host pointer is copied into `slot`.
+template <typename T>
+inline int stage_in(rh_ctx *ctx, const T *p, size_t count, int slot, const T **out) {
+    if (!p) {
+        *out = nullptr;
+        return RH_OK;
+    }
+    if (is_device_ptr(p)) {
+        *out = p;
+        return RH_OK;
+    }
+    void *d = nullptr;
+    RH_TRY(scratch(ctx, slot, count * sizeof(T), &d));
+    RH_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = static_cast<const T *>(d);
+    return RH_OK;
+}
+
+// Output staging: device pointer in place; host pointer gets a scratch buffer and a
+// finish() that copies it back.
+template <typename T>
+struct OutBuf {
+    T *dev = nullptr;
+    T *user = nullptr;
+    size_t count = 0;
+    bool staged = false;
+    int prepare(rh_ctx *ctx, T *p, size_t n, int slot) {
+        user = p;
+        count = n;
+        if (!p) return RH_OK;
+        if (is_device_ptr(p)) {
+            dev = p;
+            return RH_OK;
+        }
+        void *d = nullptr;
+        RH_TRY(scratch(ctx, slot, n * sizeof(T), &d));
+        dev = static_cast<T *>(d);
+        staged = true;
+        return RH_OK;
+    }
+    int finish(rh_ctx *ctx) {
+        if (staged && count)
+            RH_CUDA(ctx, cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        return RH_OK;
+    }
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace rh

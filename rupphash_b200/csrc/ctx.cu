@@ -1,0 +1,289 @@
+// ctx.cu -- context lifetime, pinned helpers and the on-device peak microbenchmarks that give
+// the Hamming roofline its denominator (MEASURED_PEAKS.json has no integer-pipe figure).
+#include "common.cuh"
+
+extern "C" {
+
+int rh_ctx_create(int device, rh_ctx **out) {
+    if (!out) return RH_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return RH_ECUDA;  // no CPU fallback: without a device there is no context
+    }
+    if (device < 0 || device >= count) return RH_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return RH_ECUDA;
+    rh_ctx *ctx = new (std::nothrow) rh_ctx();
+    if (!ctx) return RH_ENOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        rh_ctx_destroy(ctx);
+        return RH_ECUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return RH_OK;
+}
+
+int rh_ctx_destroy(rh_ctx *ctx) {
+    if (!ctx) return RH_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < rh_ctx::kSlots; i++)
+        if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    for (int i = 0; i < rh_ctx::kHostSlots; i++)
+        if (ctx->hslot_ptr[i]) cudaFreeHost(ctx->hslot_ptr[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return RH_OK;
+}
+
+int rh_ctx_set_stream(rh_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return RH_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return RH_OK;
+}
+
+int rh_ctx_sync(rh_ctx *ctx) {
+    if (!ctx) return RH_EINVAL;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RH_OK;
+}
+
+const char *rh_last_error(const rh_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+const char *rh_version(void) { return "rupphash_b200 0.1 (sm_100a)"; }
+
+uint64_t rh_kernel_launches(const rh_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rh_last_kernel_time(const rh_ctx *ctx, double *ms, double *units) {
+    if (!ctx) return RH_EINVAL;
+    if (ms) *ms = ctx->last_ms;
+    if (units) *units = ctx->last_units;
+    return RH_OK;
+}
+
+int rh_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return RH_EINVAL;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return RH_ENOMEM;
+    }
+    return RH_OK;
+}
+
+int rh_free_pinned(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return RH_ECUDA;
+    }
+    return RH_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------- peaks ----
+namespace {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_ITERS = 4096;
+constexpr int PK_CHAINS = 8;
+
+// Dependency-free-ish POPC stream: 8 independent chains per thread, each POPC feeds a cheap
+// add so that the compiler cannot fold it; only POPC is counted.
+__global__ void __launch_bounds__(PK_THREADS) peak_popc_kernel(uint32_t *out, uint32_t seed) {
+    uint32_t v[PK_CHAINS], acc[PK_CHAINS];
+#pragma unroll
+    for (int k = 0; k < PK_CHAINS; k++) {
+        v[k] = seed * (threadIdx.x + 1) + 0x9E3779B9u * (k + 1) + blockIdx.x;
+        acc[k] = 0;
+    }
+    for (int it = 0; it < PK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < PK_CHAINS; k++) {
+            uint32_t p;
+            asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(v[k]));
+            v[k] += p;  // IADD on the alu pipe, 1 per POPC
+            acc[k] ^= p;
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < PK_CHAINS; k++) r += acc[k] + v[k];
+    if (r == 0x12345u) out[0] = r;
+}
+
+__global__ void __launch_bounds__(PK_THREADS) peak_lop3_kernel(uint32_t *out, uint32_t seed) {
+    uint32_t v[PK_CHAINS], w[PK_CHAINS];
+#pragma unroll
+    for (int k = 0; k < PK_CHAINS; k++) {
+        v[k] = seed * (threadIdx.x + 1) + 0x9E3779B9u * (k + 1) + blockIdx.x;
+        w[k] = v[k] * 2654435761u;
+    }
+    for (int it = 0; it < PK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < PK_CHAINS; k++) {
+            // two dependent LOP3s per chain step (xor3, then majority), 2 counted ops
+            uint32_t s, c;
+            asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(v[k]), "r"(w[k]), "r"(seed));
+            asm volatile("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c) : "r"(s), "r"(w[k]), "r"(v[k]));
+            v[k] = s;
+            w[k] = c;
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < PK_CHAINS; k++) r += w[k] ^ v[k];
+    if (r == 0x12345u) out[0] = r;
+}
+
+__global__ void peak_copy_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = in[i];
+}
+
+}  // namespace
+
+extern "C" int rh_measure_peaks(rh_ctx *ctx, double out[4]) {
+    if (!ctx || !out) return RH_EINVAL;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    RH_TRY(rh::scratch(ctx, rh::S_W0, 256, &d));
+    cudaStream_t st = ctx->stream;
+    const int blocks = ctx->sm_count * 8;
+    float ms = 0.f;
+    auto best_of = [&](auto launch, double ops, double *res) -> int {
+        double best = 1e30;
+        for (int rep = 0; rep < 5; rep++) {
+            RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+            launch();
+            RH_LAUNCHED(ctx, "peak kernel");
+            RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+            RH_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+            RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        *res = ops / (best * 1e-3);
+        return RH_OK;
+    };
+    const double lanes = (double)blocks * PK_THREADS;
+    RH_TRY(best_of([&] { peak_popc_kernel<<<blocks, PK_THREADS, 0, st>>>((uint32_t *)d, 12345u); },
+                   lanes * PK_ITERS * PK_CHAINS, &out[0]));
+    RH_TRY(best_of([&] { peak_lop3_kernel<<<blocks, PK_THREADS, 0, st>>>((uint32_t *)d, 12345u); },
+                   lanes * PK_ITERS * PK_CHAINS * 2.0, &out[1]));
+    // pinned H2D and device copy over 512 MiB
+    const size_t bytes = size_t(512) << 20;
+    void *da = nullptr, *db = nullptr, *h = nullptr;
+    RH_TRY(rh::scratch(ctx, rh::S_W1, bytes, &da));
+    RH_TRY(rh::scratch(ctx, rh::S_W2, bytes, &db));
+    RH_TRY(rh::host_scratch(ctx, 0, bytes, &h));
+    memset(h, 1, bytes);
+    {
+        double best = 1e30;
+        for (int rep = 0; rep < 4; rep++) {
+            RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+            RH_CUDA(ctx, cudaMemcpyAsync(da, h, bytes, cudaMemcpyHostToDevice, st));
+            RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+            RH_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+            RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out[2] = bytes / (best * 1e-3) / 1e9;
+    }
+    RH_TRY(best_of([&] { peak_copy_kernel<<<ctx->sm_count * 16, 512, 0, st>>>((const uint4 *)da, (uint4 *)db, bytes / 16); },
+                   2.0 * bytes / 1e9, &out[3]));
+    return RH_OK;
+}
+
+// ------------------------------------------------------- pHash bit operations ----
+// phash.rs:150-255.  Bit index of pixel (x, y) is 63 - (8y + x) (phash.rs:74-80).
+namespace {
+inline int bit_of(uint64_t h, int x, int y) { return (int)((h >> (63 - (8 * y + x))) & 1ull); }
+inline uint64_t put(int b, int x, int y) { return (uint64_t)(b & 1) << (63 - (8 * y + x)); }
+}  // namespace
+
+extern "C" {
+
+// rot90: dst(x, y) = src(y, x) (a transpose), complemented where dst x is odd (phash.rs:150-171)
+uint64_t rh_phash_rotate_90(uint64_t h) {
+    uint64_t r = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) r |= put(bit_of(h, y, x) ^ (x & 1), x, y);
+    return r;
+}
+
+// rot180: same position, complemented where (x + y) is odd (phash.rs:175-188)
+uint64_t rh_phash_rotate_180(uint64_t h) {
+    uint64_t r = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) r |= put(bit_of(h, x, y) ^ ((x + y) & 1), x, y);
+    return r;
+}
+
+// rot270: transpose, complemented where dst y is odd (phash.rs:191-212)
+uint64_t rh_phash_rotate_270(uint64_t h) {
+    uint64_t r = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) r |= put(bit_of(h, y, x) ^ (y & 1), x, y);
+    return r;
+}
+
+// flip: same position, complemented where x is odd (phash.rs:220-230)
+uint64_t rh_phash_flip_horizontal(uint64_t h) {
+    uint64_t r = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) r |= put(bit_of(h, x, y) ^ (x & 1), x, y);
+    return r;
+}
+
+// phash.rs:242-255: [h, r90, r180, r270, f, r90(f), r180(f), r270(f)]
+void rh_phash_dihedral(uint64_t h, uint64_t out[8]) {
+    uint64_t f = rh_phash_flip_horizontal(h);
+    out[0] = h;
+    out[1] = rh_phash_rotate_90(h);
+    out[2] = rh_phash_rotate_180(h);
+    out[3] = rh_phash_rotate_270(h);
+    out[4] = f;
+    out[5] = rh_phash_rotate_90(f);
+    out[6] = rh_phash_rotate_180(f);
+    out[7] = rh_phash_rotate_270(f);
+}
+
+// phash.rs:137-143: min over the four rotations
+uint64_t rh_phash_rotation_invariant(uint64_t h) {
+    uint64_t m = h, r;
+    r = rh_phash_rotate_90(h);
+    if (r < m) m = r;
+    r = rh_phash_rotate_180(h);
+    if (r < m) m = r;
+    r = rh_phash_rotate_270(h);
+    if (r < m) m = r;
+    return m;
+}
+
+}  // extern "C"

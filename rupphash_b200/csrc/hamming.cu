@@ -1,0 +1,604 @@
+// hamming.cu -- hot path #2: all-pairs Hamming search under a threshold + device union-find.
+//
+// Replaces the edge phase and union-find of scanner::group_files_generic
+// (scanner.rs:1640-1817) and HammingHash::hamming_distance (hamminghash.rs:34-36, :55-58).
+// The reference finds the pairs through Multi-Index-Hashing bucket probes; for every allowed
+// similarity (<= 63) the pigeonhole argument makes that set identical to the all-pairs set
+// (SURVEY.md F3), which is what the tiles below enumerate.
+//
+// Kernel shape (hamming_tiles_kernel): a CTA owns a tile of HT_TQ query rows x HT_TC candidates.
+// Candidates (8 x u32 each) sit in shared memory and are read with warp-broadcast LDS.128;
+// every thread keeps HT_RQ query rows in registers, so one candidate fetch feeds HT_RQ pairs.
+// A pair costs 8 XOR + a 4-step carry-save compression (8 LOP3) + 4 POPC instead of 8 POPC:
+// POPC issues at a quarter of the LOP3 rate, so trading POPCs for LOP3s balances the two pipes.
+// Pairs under the threshold are rare; they take a divergent slow path that applies the exact
+// edge rule (j > i, low-confidence => distance 0 only) and hooks the union-find.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+#include "unionfind.cuh"
+
+namespace {
+
+constexpr int HT_THREADS = 256;
+constexpr int HT_RQ = 4;                     // query rows per thread
+constexpr int HT_TQ = HT_THREADS * HT_RQ;    // query rows per CTA tile
+constexpr int HT_TC = 1024;                  // candidates per CTA tile (32 KB of shared memory)
+
+struct GroupArgs {
+    const uint32_t *cand;     // [nc_pad][W] dense candidate hashes, zero padded to HT_TC rows
+    const uint32_t *qry;      // [nq_pad][W] query rows ordered by file, 0xFF padded to HT_TQ rows
+    const uint32_t *qfile;    // [nq_pad] dense file id of each query row (0xFFFFFFFF = padding)
+    const uint8_t *lc;        // [nc] low-confidence flag per dense file, or nullptr
+    uint32_t *parent;         // [nc] union-find forest over dense ids
+    unsigned long long *edge_count;
+    uint2 *edges;             // optional edge sink (dense ids), capacity edges_cap
+    unsigned long long edges_cap;
+    unsigned long long *edges_n;
+    uint32_t nc, nq, threshold;
+    int rank, world;
+};
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// popcount of a 256-bit XOR: carry-save adders fold 8 words into weights 1,1,2,4 -> 4 POPC.
+//   p(x0..x2) = p(s0) + 2 p(c0);  p(x3..x5) = p(s1) + 2 p(c1);  p(s0,s1,x6) = p(s2) + 2 p(c2)
+//   p(c0,c1,c2) = p(t0) + 2 p(d0)   =>  total = p(s2) + p(x7) + 2 p(t0) + 4 p(d0)
+__device__ __forceinline__ uint32_t dist256(const uint32_t (&q)[8], const uint4 &a, const uint4 &b) {
+    uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
+    uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    uint32_t t0 = xor3(c0, c1, c2), d0 = maj3(c0, c1, c2);
+    return (__popc(s2) + __popc(x7)) + 2u * __popc(t0) + 4u * __popc(d0);
+}
+
+// Rare path, kept out of line so that none of its address arithmetic is hoisted into the hot
+// loop.  `g` points at the CTA's shared-memory copy of the arguments.
+__device__ __noinline__ uint32_t slow_hit(const GroupArgs *g, uint32_t d, uint32_t qf, uint32_t cj) {
+    // exact edge rule of scanner.rs:1712-1724 in dense index space
+    if (qf == 0xFFFFFFFFu || cj >= g->nc || cj <= qf) return 0;
+    uint32_t lim = g->threshold;
+    if (g->lc && (g->lc[qf] | g->lc[cj])) lim = 0;  // scanner.rs:1699, :1721
+    if (d > lim) return 0;
+    if (g->edges) {
+        unsigned long long k = atomicAdd(g->edges_n, 1ull);
+        if (k < g->edges_cap) g->edges[k] = make_uint2(qf, cj);
+    }
+    rh::uf_unite(g->parent, qf, cj);
+    return 1;
+}
+
+// owner of a tile among `world` ranks: cyclic over anti-diagonals keeps every rank's share of
+// the upper triangle within one tile row of the others
+__device__ __host__ __forceinline__ int tile_owner(uint32_t qb, uint32_t cb, int world) {
+    return (int)((qb + cb) % (uint32_t)world);
+}
+
+__global__ void __launch_bounds__(HT_THREADS) hamming_tiles_kernel(const GroupArgs g) {
+    const uint32_t cb = blockIdx.x, qb = blockIdx.y;
+    if (tile_owner(qb, cb, g.world) != g.rank) return;
+    const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
+    const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
+    // rows are ordered by file: the first row has the smallest file id of the block.  A tile
+    // whose last candidate is not above it holds no pair with j > i (scanner.rs:1712-1714).
+    if (!(c1 - 1 > g.qfile[q0])) return;
+
+    __shared__ uint4 s_cand[HT_TC * 2];
+    __shared__ GroupArgs s_g;
+    if (threadIdx.x == 0) s_g = g;
+    const uint4 *cand4 = reinterpret_cast<const uint4 *>(g.cand) + (size_t)c0 * 2;
+    for (int i = threadIdx.x; i < HT_TC * 2; i += HT_THREADS) s_cand[i] = cand4[i];
+
+    uint32_t q[HT_RQ][8];
+    uint32_t qf[HT_RQ];
+#pragma unroll
+    for (int r = 0; r < HT_RQ; r++) {
+        const uint32_t row = q0 + r * HT_THREADS + threadIdx.x;
+        const uint4 *p = reinterpret_cast<const uint4 *>(g.qry) + (size_t)row * 2;
+        uint4 a = p[0], b = p[1];
+        q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w;
+        q[r][4] = b.x; q[r][5] = b.y; q[r][6] = b.z; q[r][7] = b.w;
+        qf[r] = g.qfile[row];
+    }
+    __syncthreads();
+
+    const uint32_t T = g.threshold;
+    const int cn = (int)(c1 - c0);
+    uint32_t local_edges = 0;
+#pragma unroll 2
+    for (int c = 0; c < cn; c++) {
+        const uint4 a = s_cand[2 * c], b = s_cand[2 * c + 1];
+        uint32_t d[HT_RQ];
+#pragma unroll
+        for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+        uint32_t m = d[0];
+#pragma unroll
+        for (int r = 1; r < HT_RQ; r++) m = min(m, d[r]);
+        if (m <= T) {
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++)
+                if (d[r] <= T) local_edges += slow_hit(&s_g, d[r], qf[r], c0 + c);
+        }
+    }
+    // one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_edges += __shfl_xor_sync(0xFFFFFFFFu, local_edges, o);
+    if ((threadIdx.x & 31) == 0 && local_edges) atomicAdd(g.edge_count, (unsigned long long)local_edges);
+}
+
+// 64-bit hashes (hamminghash.rs:23-41): 2 words per hash, one thread per query row, the same
+// tile ownership.  Throughput is not a target here (no reference caller groups u64 hashes).
+__global__ void __launch_bounds__(HT_THREADS) hamming_tiles_u64_kernel(const GroupArgs g) {
+    const uint32_t cb = blockIdx.x, qb = blockIdx.y;
+    if (tile_owner(qb, cb, g.world) != g.rank) return;
+    const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
+    const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
+    if (!(c1 - 1 > g.qfile[q0])) return;
+    __shared__ uint2 s_cand[HT_TC];
+    __shared__ GroupArgs s_g;
+    if (threadIdx.x == 0) s_g = g;
+    const uint2 *cand2 = reinterpret_cast<const uint2 *>(g.cand) + c0;
+    for (int i = threadIdx.x; i < HT_TC; i += HT_THREADS) s_cand[i] = cand2[i];
+    uint2 q[HT_RQ];
+    uint32_t qf[HT_RQ];
+#pragma unroll
+    for (int r = 0; r < HT_RQ; r++) {
+        const uint32_t row = q0 + r * HT_THREADS + threadIdx.x;
+        q[r] = reinterpret_cast<const uint2 *>(g.qry)[row];
+        qf[r] = g.qfile[row];
+    }
+    __syncthreads();
+    const uint32_t T = g.threshold;
+    const int cn = (int)(c1 - c0);
+    uint32_t local_edges = 0;
+    for (int c = 0; c < cn; c++) {
+        const uint2 a = s_cand[c];
+#pragma unroll
+        for (int r = 0; r < HT_RQ; r++) {
+            uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
+            if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_edges += __shfl_xor_sync(0xFFFFFFFFu, local_edges, o);
+    if ((threadIdx.x & 31) == 0 && local_edges) atomicAdd(g.edge_count, (unsigned long long)local_edges);
+}
+
+// ------------------------------------------------------------ preparation ----
+
+// valid[i] (file has a hash) and nv[i] (number of query rows of file i); entry n is 0 so that
+// the exclusive scans end with the totals.
+__global__ void flags_kernel(const uint8_t *has_hash, const uint8_t *n_variants, int has_variants,
+                             uint32_t n, uint32_t *valid, uint32_t *nv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t v = 0, q = 0;
+    if (i < n) {
+        v = has_hash ? (has_hash[i] != 0) : 1u;
+        if (v) q = has_variants ? (n_variants ? min((uint32_t)n_variants[i], 8u) : 8u) : 1u;
+    }
+    valid[i] = v;
+    nv[i] = q;
+}
+
+__device__ __forceinline__ uint32_t load_le32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// One thread per (file, word): scatters candidate words, query rows, ids and flags into the
+// dense arrays.  Bytes are read one by one, so the caller's buffers need no alignment.
+template <int W>
+__global__ void scatter_kernel(const uint8_t *hashes, const uint8_t *variants, const uint8_t *low_conf,
+                               uint32_t n, const uint32_t *valid, const uint32_t *dpos,
+                               const uint32_t *nv, const uint32_t *qoff, uint32_t *cand,
+                               uint32_t *cand_idx, uint8_t *lc, uint32_t *qry, uint32_t *qfile) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = t / W, w = t % W;
+    if (i >= n || !valid[i]) return;
+    const uint32_t k = dpos[i];
+    cand[(size_t)k * W + w] = load_le32(hashes + (size_t)i * (W * 4) + w * 4);
+    if (w == 0) {
+        cand_idx[k] = i;
+        if (lc) lc[k] = low_conf[i] ? 1 : 0;
+    }
+    const uint32_t cnt = nv[i], qo = qoff[i];
+    for (uint32_t v = 0; v < cnt; v++) {
+        const uint8_t *src = variants ? variants + ((size_t)i * 8 + v) * (W * 4) : hashes + (size_t)i * (W * 4);
+        qry[(size_t)(qo + v) * W + w] = load_le32(src + w * 4);
+        if (w == 0) qfile[qo + v] = k;
+    }
+}
+
+__global__ void iota_kernel(uint32_t *p, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// label of sparse file i = sparse index of the root of its dense id (files without a hash
+// are their own label, scanner.rs:1658-1662 keeps them out of the search).
+__global__ void labels_kernel(uint32_t *parent, const uint32_t *valid, const uint32_t *dpos,
+                              const uint32_t *cand_idx, uint32_t n, uint32_t *out_label) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_label[i] = valid[i] ? cand_idx[rh::uf_find(parent, dpos[i])] : i;
+}
+
+__global__ void merge_kernel(const uint32_t *parents, uint32_t n, int world, uint32_t *parent) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * world) return;
+    uint32_t i = (uint32_t)(t % n);
+    uint32_t p = parents[t];
+    if (p != i && p < n) rh::uf_unite(parent, i, p);
+}
+
+__global__ void flatten_kernel(uint32_t *parent, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rh::uf_find(parent, i);
+}
+
+template <int W>
+__global__ void distances_kernel(const uint8_t *a, const uint8_t *b, size_t n, uint32_t *out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++)
+        d += __popc(load_le32(a + i * (W * 4) + w * 4) ^ load_le32(b + i * (W * 4) + w * 4));
+    out[i] = d;
+}
+
+__global__ void edges_to_sparse_kernel(uint2 *edges, unsigned long long cap, const unsigned long long *n_edges,
+                                       const uint32_t *cand_idx) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long m = *n_edges < cap ? *n_edges : cap;
+    if (k >= m) return;
+    uint2 e = edges[k];
+    edges[k] = make_uint2(cand_idx[e.x], cand_idx[e.y]);
+}
+
+struct Prepared {
+    GroupArgs g;
+    const uint32_t *valid, *dpos, *cand_idx;
+    uint32_t n_qb, n_cb;
+};
+
+// Builds the dense candidate / query arrays on the device.  W = words per hash (8 or 2).
+template <int W>
+int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+            const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+            int rank, int world, Prepared *out) {
+    using namespace rh;
+    cudaStream_t st = ctx->stream;
+    const size_t hb = W * 4;
+    const uint8_t *d_hashes, *d_has, *d_var, *d_nv, *d_lc;
+    RH_TRY(stage_in(ctx, hashes, (size_t)n * hb, S_IN0, &d_hashes));
+    RH_TRY(stage_in(ctx, has_hash, (size_t)n, S_IN1, &d_has));
+    RH_TRY(stage_in(ctx, variants, (size_t)n * 8 * hb, S_IN2, &d_var));
+    RH_TRY(stage_in(ctx, n_variants, (size_t)n, S_IN3, &d_nv));
+    RH_TRY(stage_in(ctx, low_conf, (size_t)n, S_IN4, &d_lc));
+
+    uint32_t *valid, *nv, *dpos, *qoff;
+    void *p;
+    RH_TRY(scratch(ctx, S_W0, (size_t)(n + 1) * 4, &p)); valid = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W1, (size_t)(n + 1) * 4, &p)); nv = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W2, (size_t)(n + 1) * 4, &p)); dpos = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W3, (size_t)(n + 1) * 4, &p)); qoff = (uint32_t *)p;
+    flags_kernel<<<cdiv(n + 1, 256), 256, 0, st>>>(d_has, d_nv, d_var != nullptr, (uint32_t)n, valid, nv);
+    RH_LAUNCHED(ctx, "flags_kernel");
+    size_t tmp_bytes = 0;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, valid, dpos, (int)(n + 1), st));
+    void *tmp;
+    RH_TRY(scratch(ctx, S_W4, tmp_bytes, &tmp));
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, valid, dpos, (int)(n + 1), st));
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nv, qoff, (int)(n + 1), st));
+    ctx->launches += 2;
+    uint32_t totals[2];
+    RH_CUDA(ctx, cudaMemcpyAsync(&totals[0], dpos + n, 4, cudaMemcpyDeviceToHost, st));
+    RH_CUDA(ctx, cudaMemcpyAsync(&totals[1], qoff + n, 4, cudaMemcpyDeviceToHost, st));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t nc = totals[0], nq = totals[1];
+    const size_t nc_pad = (size_t)cdiv(nc ? nc : 1, HT_TC) * HT_TC;
+    const size_t nq_pad = (size_t)cdiv(nq ? nq : 1, HT_TQ) * HT_TQ;
+
+    uint32_t *cand, *cand_idx, *qry, *qfile, *parent;
+    uint8_t *lc = nullptr;
+    unsigned long long *counters;
+    RH_TRY(scratch(ctx, S_W5, nc_pad * hb, &p)); cand = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W6, nc_pad * 4, &p)); cand_idx = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W7, nq_pad * hb, &p)); qry = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W8, nq_pad * 4, &p)); qfile = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W9, nc_pad * 4, &p)); parent = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W10, 64, &p)); counters = (unsigned long long *)p;
+    if (d_lc) {
+        RH_TRY(scratch(ctx, S_W11, nc_pad, &p));
+        lc = (uint8_t *)p;
+    }
+    RH_CUDA(ctx, cudaMemsetAsync(cand, 0, nc_pad * hb, st));
+    RH_CUDA(ctx, cudaMemsetAsync(qry, 0xFF, nq_pad * hb, st));
+    RH_CUDA(ctx, cudaMemsetAsync(qfile, 0xFF, nq_pad * 4, st));
+    RH_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, st));
+    if (n > 0) {
+        scatter_kernel<W><<<cdiv((size_t)n * W, 256), 256, 0, st>>>(d_hashes, d_var, d_lc, (uint32_t)n, valid, dpos, nv,
+                                                                    qoff, cand, cand_idx, lc, qry, qfile);
+        RH_LAUNCHED(ctx, "scatter_kernel");
+    }
+    iota_kernel<<<cdiv(nc_pad, 256), 256, 0, st>>>(parent, (uint32_t)nc_pad);
+    RH_LAUNCHED(ctx, "iota_kernel");
+
+    GroupArgs &g = out->g;
+    g.cand = cand;
+    g.qry = qry;
+    g.qfile = qfile;
+    g.lc = lc;
+    g.parent = parent;
+    g.edge_count = counters;
+    g.edges = nullptr;
+    g.edges_cap = 0;
+    g.edges_n = counters + 1;
+    g.nc = nc;
+    g.nq = nq;
+    g.threshold = similarity;
+    g.rank = rank;
+    g.world = world;
+    out->valid = valid;
+    out->dpos = dpos;
+    out->cand_idx = cand_idx;
+    out->n_cb = (uint32_t)(nc_pad / HT_TC);
+    out->n_qb = (uint32_t)(nq_pad / HT_TQ);
+    return RH_OK;
+}
+
+template <int W>
+int run_tiles(rh_ctx *ctx, const Prepared &pr) {
+    cudaStream_t st = ctx->stream;
+    ctx->last_ms = 0.0;
+    ctx->last_units = 0.0;
+    if (pr.g.nc < 2 || pr.g.nq == 0) return RH_OK;
+    if (pr.n_qb > 65535u) return rh::fail(ctx, RH_EUNSUPPORTED, "more than 65535 x 1024 query rows");
+    dim3 grid(pr.n_cb, pr.n_qb);
+    RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    if (W == 8)
+        hamming_tiles_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
+    else
+        hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
+    RH_LAUNCHED(ctx, "hamming_tiles_kernel");
+    RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    RH_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+    float ms = 0.f;
+    RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->last_ms = ms;
+    return RH_OK;
+}
+
+template <int W>
+int group_impl(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+               const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+               uint32_t max_similarity, int rank, int world, uint32_t *out_label, uint64_t *out_edge_count,
+               uint32_t *out_edges, size_t edges_cap) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || n > 0x7FFFFFF0ll) return fail(ctx, RH_EINVAL, "n out of range");
+    if (similarity > max_similarity) return fail(ctx, RH_EINVAL, "similarity above 63 (scanner.rs:1650-1655)");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, RH_EINVAL, "bad rank/world");
+    if ((n > 0 && !hashes) || (n_variants && !variants)) return fail(ctx, RH_EINVAL, "null hashes");
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (out_edge_count) *out_edge_count = 0;
+    if (n == 0) return RH_OK;
+    Prepared pr;
+    RH_TRY(prepare<W>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, rank, world, &pr));
+    OutBuf<uint32_t> lab;
+    RH_TRY(lab.prepare(ctx, out_label, (size_t)n, S_OUT0));
+    OutBuf<uint32_t> edg;
+    if (out_edges && edges_cap) {
+        RH_TRY(edg.prepare(ctx, out_edges, edges_cap * 2, S_OUT1));
+        pr.g.edges = reinterpret_cast<uint2 *>(edg.dev);
+        pr.g.edges_cap = edges_cap;
+    }
+    RH_TRY(run_tiles<W>(ctx, pr));
+    if (lab.dev) {
+        labels_kernel<<<cdiv(n, 256), 256, 0, st>>>(pr.g.parent, pr.valid, pr.dpos, pr.cand_idx, (uint32_t)n, lab.dev);
+        RH_LAUNCHED(ctx, "labels_kernel");
+        RH_TRY(lab.finish(ctx));
+    }
+    if (edg.dev) {
+        // dense ids -> file indices (the edge list itself is unordered)
+        edges_to_sparse_kernel<<<cdiv(edges_cap, 256), 256, 0, st>>>(pr.g.edges, pr.g.edges_cap, pr.g.edges_n,
+                                                                     pr.cand_idx);
+        RH_LAUNCHED(ctx, "edges_to_sparse_kernel");
+        RH_TRY(edg.finish(ctx));
+    }
+    unsigned long long counts[2] = {0, 0};
+    RH_CUDA(ctx, cudaMemcpyAsync(counts, pr.g.edge_count, 16, cudaMemcpyDeviceToHost, st));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out_edge_count) *out_edge_count = counts[0];
+    return RH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rh_hamming_group(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                     const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                     uint32_t *out_label, uint64_t *out_edge_count) {
+    return group_impl<8>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, RH_MAX_SIMILARITY_256, 0, 1,
+                         out_label, out_edge_count, nullptr, 0);
+}
+
+int rh_hamming_group_shard(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                           const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                           int rank, int world, uint32_t *out_parent, uint64_t *out_edge_count) {
+    return group_impl<8>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, RH_MAX_SIMILARITY_256, rank,
+                         world, out_parent, out_edge_count, nullptr, 0);
+}
+
+int rh_hamming_group_u64(rh_ctx *ctx, const uint64_t *hashes, const uint8_t *has_hash, const uint64_t *variants,
+                         const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                         uint32_t *out_label, uint64_t *out_edge_count) {
+    return group_impl<2>(ctx, reinterpret_cast<const uint8_t *>(hashes), has_hash,
+                         reinterpret_cast<const uint8_t *>(variants), n_variants, low_conf, n, similarity,
+                         RH_MAX_SIMILARITY_256, 0, 1, out_label, out_edge_count, nullptr, 0);
+}
+
+int rh_uf_merge(rh_ctx *ctx, const uint32_t *parents, int world, int64_t n, uint32_t *out_label) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || n > 0x7FFFFFF0ll || world < 1 || (n > 0 && (!parents || !out_label)))
+        return fail(ctx, RH_EINVAL, "rh_uf_merge: bad arguments");
+    if (n == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t *d_par;
+    RH_TRY(stage_in(ctx, parents, (size_t)n * world, S_IN0, &d_par));
+    void *p;
+    RH_TRY(scratch(ctx, S_W9, (size_t)n * 4, &p));
+    uint32_t *parent = (uint32_t *)p;
+    OutBuf<uint32_t> lab;
+    RH_TRY(lab.prepare(ctx, out_label, (size_t)n, S_OUT0));
+    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n);
+    RH_LAUNCHED(ctx, "iota_kernel");
+    merge_kernel<<<cdiv((size_t)n * world, 256), 256, 0, st>>>(d_par, (uint32_t)n, world, parent);
+    RH_LAUNCHED(ctx, "merge_kernel");
+    flatten_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n, lab.dev);
+    RH_LAUNCHED(ctx, "flatten_kernel");
+    RH_TRY(lab.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    return RH_OK;
+}
+
+int rh_hamming_distances(rh_ctx *ctx, const uint8_t *a, const uint8_t *b, int64_t n, uint32_t *out) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(ctx, RH_EINVAL, "rh_hamming_distances: bad arguments");
+    if (n == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint8_t *da, *db;
+    RH_TRY(stage_in(ctx, a, (size_t)n * 32, S_IN0, &da));
+    RH_TRY(stage_in(ctx, b, (size_t)n * 32, S_IN1, &db));
+    OutBuf<uint32_t> o;
+    RH_TRY(o.prepare(ctx, out, (size_t)n, S_OUT0));
+    distances_kernel<8><<<cdiv(n, 256), 256, 0, st>>>(da, db, (size_t)n, o.dev);
+    RH_LAUNCHED(ctx, "distances_kernel");
+    RH_TRY(o.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    return RH_OK;
+}
+
+int rh_hamming_distances_u64(rh_ctx *ctx, const uint64_t *a, const uint64_t *b, int64_t n, uint32_t *out) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(ctx, RH_EINVAL, "rh_hamming_distances_u64: bad arguments");
+    if (n == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint8_t *da, *db;
+    RH_TRY(stage_in(ctx, reinterpret_cast<const uint8_t *>(a), (size_t)n * 8, S_IN0, &da));
+    RH_TRY(stage_in(ctx, reinterpret_cast<const uint8_t *>(b), (size_t)n * 8, S_IN1, &db));
+    OutBuf<uint32_t> o;
+    RH_TRY(o.prepare(ctx, out, (size_t)n, S_OUT0));
+    distances_kernel<2><<<cdiv(n, 256), 256, 0, st>>>(da, db, (size_t)n, o.dev);
+    RH_LAUNCHED(ctx, "distances_kernel");
+    RH_TRY(o.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    return RH_OK;
+}
+
+int rh_hamming_edges(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                     const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                     uint32_t *out_edges, size_t edges_cap, uint64_t *out_edge_count) {
+    return group_impl<8>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, RH_MAX_SIMILARITY_256,
+                         0, 1, nullptr, out_edge_count, out_edges, edges_cap);
+}
+
+int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits, uint32_t max_dist,
+                   uint32_t *members, size_t members_cap, uint32_t *group_offsets, size_t groups_cap,
+                   size_t *n_groups) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (!n_groups || (width_bits != 64 && width_bits != 256) || n < 0 || (n > 0 && !hashes) || !group_offsets ||
+        groups_cap < 1)
+        return fail(ctx, RH_EINVAL, "rh_find_groups: bad arguments");
+    *n_groups = 0;
+    group_offsets[0] = 0;
+    if (n < 2) return RH_OK;
+    if (max_dist > (uint32_t)width_bits) max_dist = (uint32_t)width_bits;
+    // Device: the exact adjacency as an unordered list of (i < j) pairs.  The list is sized by a
+    // first guess and the search repeated once if it overflowed.
+    std::vector<uint32_t> edges;
+    size_t cap = (size_t)n * 4 + (1u << 20);
+    uint64_t count = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        try {
+            edges.assign(cap * 2, 0u);
+        } catch (const std::bad_alloc &) {
+            return fail(ctx, RH_ENOMEM, "rh_find_groups: edge list");
+        }
+        int s = width_bits == 256
+                    ? group_impl<8>(ctx, hashes, nullptr, nullptr, nullptr, nullptr, n, max_dist, 256, 0, 1, nullptr,
+                                    &count, edges.data(), cap)
+                    : group_impl<2>(ctx, hashes, nullptr, nullptr, nullptr, nullptr, n, max_dist, 64, 0, 1, nullptr,
+                                    &count, edges.data(), cap);
+        if (s != RH_OK) return s;
+        if (count <= cap) break;
+        cap = (size_t)count;
+    }
+    // Host: CSR adjacency (both directions, ascending), then the sequential greedy star
+    // clustering of hamminghash.rs:245-270 -- sequential in the reference too.
+    std::vector<uint32_t> deg((size_t)n + 1, 0u);
+    for (uint64_t k = 0; k < count; k++) {
+        deg[edges[2 * k] + 1]++;
+        deg[edges[2 * k + 1] + 1]++;
+    }
+    for (int64_t i = 0; i < n; i++) deg[i + 1] += deg[i];
+    std::vector<uint32_t> adj((size_t)count * 2), fill(deg.begin(), deg.end() - 1);
+    for (uint64_t k = 0; k < count; k++) {
+        uint32_t a = edges[2 * k], b = edges[2 * k + 1];
+        adj[fill[a]++] = b;
+        adj[fill[b]++] = a;
+    }
+    std::vector<uint8_t> visited((size_t)n, 0);
+    size_t ng = 0, nm = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (visited[i] || deg[i + 1] == deg[i]) continue;
+        visited[i] = 1;
+        std::sort(adj.begin() + deg[i], adj.begin() + deg[i + 1]);
+        size_t len = 1;
+        for (uint32_t k = deg[i]; k < deg[i + 1]; k++)
+            if (!visited[adj[k]]) len++;
+        if (len > 1) {
+            if (ng + 1 >= groups_cap || nm + len > members_cap || !members)
+                return fail(ctx, RH_EINVAL, "rh_find_groups: output capacity too small");
+            members[nm++] = (uint32_t)i;
+        }
+        for (uint32_t k = deg[i]; k < deg[i + 1]; k++) {
+            uint32_t v = adj[k];
+            if (!visited[v]) {
+                visited[v] = 1;
+                if (len > 1) members[nm++] = v;
+            }
+        }
+        if (len > 1) {
+            group_offsets[++ng] = (uint32_t)nm;
+        }
+    }
+    *n_groups = ng;
+    return RH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// pdq.cu -- hot path #1: batched PDQ hashing (pdqhash.rs).
+//
+// Entry points: rh_pdq_hash_batch, rh_pdq_from_buffer64, rh_pdq_hash_from_coeffs,
+// rh_pdq_dihedral_from_coeffs.  Two device pipelines produce the 64 x 64 buffer:
+//   * the fused kernel of pdq_fused.cuh for planes 449..512 px wide (both BASELINE shapes),
+//   * the generic pipeline below for every other supported size: one thread walks one line
+//     exactly like box_one_d_float (pdqhash.rs:341-396), planes live in device scratch.
+// Both end in pdq_tail.cuh.  Arithmetic is f32 with explicit round-to-nearest mul/add/div
+// intrinsics, so nvcc can never contract a*b+c into an FMA (Rust never does).
+#include <math.h>
+
+#include "common.cuh"
+#include "pdq_tail.cuh"
+
+namespace rh {
+int pdq_fused_supported(int W, int H);
+int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int64_t n, int W, int H, size_t row_pitch,
+                  size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct);
+}  // namespace rh
+
+namespace {
+
+using namespace rh;
+
+// pdqhash.rs:287-304 -- computed on the host with the same f32 steps and the host libm cosf
+// (Rust's f32::cos lowers to the platform cosf), rows are frequencies 1..16.
+void host_dct_matrix(float *D) {
+    const float PI_F = 3.14159265358979323846f;
+    const float num_cols = 64.0f;
+    const float inv_sqrt_cols = 1.0f / sqrtf(num_cols);
+    const float sqrt_2 = sqrtf(2.0f);
+    for (int i = 0; i < 16; i++) {
+        const float freq = (float)(i + 1);
+        const float norm = inv_sqrt_cols * sqrt_2;
+        for (int j = 0; j < 64; j++) {
+            volatile float a = PI_F * freq;
+            volatile float b = 2.0f * (float)j + 1.0f;
+            volatile float num = a * b;
+            volatile float angle = num / (2.0f * num_cols);
+            D[i * 64 + j] = norm * cosf(angle);
+        }
+    }
+}
+
+// pdqhash.rs:268-284: (299 r + 587 g + 114 b + 500) / 1000 with truncating u32 division.
+// floor(v / 1000) == umulhi(v, ceil(2^32 / 1000)) for every v < 6.1e6 (v <= 255 500 here).
+__device__ __forceinline__ uint32_t luma601(uint32_t r, uint32_t g, uint32_t b) {
+    return __umulhi(299u * r + 587u * g + 114u * b + 500u, 4294968u);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t load_luma(const uint8_t *p) {
+    if (LAYOUT == RH_LAYOUT_LUMA8) return p[0];
+    return luma601(p[0], p[1], p[2]);
+}
+
+// Generic front end: one thread per output pixel of the (optionally 2x reduced) luma plane.
+// DOWN2 is fast_image_resize's Box convolution at an exact 2x ratio: two taps of 1/2 per axis,
+// horizontal pass first, each pass rounding half up to u8 (pdqhash.rs:203-220).
+template <int LAYOUT, bool DOWN2>
+__global__ void luma_plane_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch, int n, int W,
+                                  int H, uint8_t *__restrict__ L) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t per = (size_t)W * H;
+    if (idx >= per * n) return;
+    const size_t img = idx / per;
+    const int y = (int)((idx % per) / W), x = (int)(idx % W);
+    const uint8_t *base = px + img * img_pitch;
+    uint32_t v;
+    if (DOWN2) {
+        const uint8_t *r0 = base + (size_t)(2 * y) * row_pitch + (size_t)(2 * x) * CH;
+        const uint8_t *r1 = r0 + row_pitch;
+        const uint32_t h0 = (load_luma<LAYOUT>(r0) + load_luma<LAYOUT>(r0 + CH) + 1u) >> 1;
+        const uint32_t h1 = (load_luma<LAYOUT>(r1) + load_luma<LAYOUT>(r1 + CH) + 1u) >> 1;
+        v = (h0 + h1 + 1u) >> 1;
+    } else {
+        v = load_luma<LAYOUT>(base + (size_t)y * row_pitch + (size_t)x * CH);
+    }
+    L[idx] = (uint8_t)v;
+}
+
+// One thread per line: box_one_d_float (pdqhash.rs:341-396) verbatim -- sequential running
+// sum, IEEE division by the current window, four phases.
+template <typename Tin>
+__global__ void box_pass_kernel(const Tin *__restrict__ in, float *__restrict__ out, int n, int lines, int len,
+                                int line_stride, int elem_stride, size_t img_stride, int win) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * lines) return;
+    const size_t img = t / lines;
+    const int line = (int)(t % lines);
+    const Tin *src = in + img * img_stride + (size_t)line * line_stride;
+    float *dst = out + img * img_stride + (size_t)line * line_stride;
+    const int lim = len > 1 ? len : 1;
+    win = win < 1 ? 1 : (win > lim ? lim : win);
+    const int half = (win + 2) / 2;
+    const int phase_1 = half - 1, phase_2 = win - half + 1, phase_3 = len > win ? len - win : 0, phase_4 = half - 1;
+    size_t li = 0, ri = 0, oi = 0;
+    float sum = 0.0f, curr = 0.0f;
+    for (int i = 0; i < phase_1; i++) {
+        sum = __fadd_rn(sum, (float)src[ri]);
+        curr += 1.0f;
+        ri += elem_stride;
+    }
+    for (int i = 0; i < phase_2; i++) {
+        sum = __fadd_rn(sum, (float)src[ri]);
+        curr += 1.0f;
+        dst[oi] = __fdiv_rn(sum, curr);
+        ri += elem_stride;
+        oi += elem_stride;
+    }
+    for (int i = 0; i < phase_3; i++) {
+        sum = __fadd_rn(sum, (float)src[ri]);
+        sum = __fsub_rn(sum, (float)src[li]);
+        dst[oi] = __fdiv_rn(sum, curr);
+        li += elem_stride;
+        ri += elem_stride;
+        oi += elem_stride;
+    }
+    for (int i = 0; i < phase_4; i++) {
+        sum = __fsub_rn(sum, (float)src[li]);
+        curr -= 1.0f;
+        dst[oi] = __fdiv_rn(sum, curr);
+        li += elem_stride;
+        oi += elem_stride;
+    }
+}
+
+enum TailSrc { SRC_PLANE = 0, SRC_BUF64 = 1, SRC_COEFFS = 2 };
+
+// One CTA per image.  SRC_PLANE decimates the filtered plane (pdqhash.rs:428-443) on load.
+template <int SRC>
+__global__ void __launch_bounds__(TAIL_THREADS) pdq_tail_kernel(const float *__restrict__ src, int W, int H,
+                                                                const float *__restrict__ dct, TailOut o,
+                                                                int64_t out_offset) {
+    __shared__ TailSmem s;
+    const size_t img = blockIdx.x;
+    const size_t oimg = img + (size_t)out_offset;
+    if (SRC == SRC_COEFFS) {
+        s.C[threadIdx.x] = src[img * 256 + threadIdx.x];
+        __syncthreads();
+        tail_hashes(s, o, oimg);
+        return;
+    }
+    for (int idx = threadIdx.x; idx < 4096; idx += TAIL_THREADS) {
+        if (SRC == SRC_PLANE) {
+            const int i = idx >> 6, j = idx & 63;
+            const int ini = ((2 * i + 1) * H) / 128, inj = ((2 * j + 1) * W) / 128;
+            s.B[idx] = src[img * (size_t)W * H + (size_t)ini * W + inj];
+        } else {
+            s.B[idx] = src[img * 4096 + idx];
+        }
+    }
+    for (int idx = threadIdx.x; idx < 1024; idx += TAIL_THREADS) s.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = dct[idx];
+    __syncthreads();
+    const float q = tail_quality(s);
+    if (threadIdx.x == 0 && o.quality) o.quality[oimg] = q;
+    tail_dct(s);
+    if (o.coeffs) o.coeffs[oimg * 256 + threadIdx.x] = s.C[threadIdx.x];
+    tail_hashes(s, o, oimg);
+}
+
+int ensure_dct(rh_ctx *ctx, const float **d_dct) {
+    void *p;
+    RH_TRY(scratch(ctx, S_W13, 1024 * sizeof(float), &p));
+    if (!ctx->dct_ready) {
+        float D[1024];
+        host_dct_matrix(D);
+        RH_CUDA(ctx, cudaMemcpyAsync(p, D, sizeof D, cudaMemcpyHostToDevice, ctx->stream));
+        RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dct_ready = true;
+    }
+    *d_dct = (const float *)p;
+    return RH_OK;
+}
+
+// pdqhash.rs:224-235
+void target_dimensions(int w, int h, int max_dim, int *nw, int *nh) {
+    if (w > h) {
+        long long v = (long long)h * max_dim / w;
+        *nw = max_dim;
+        *nh = (int)(v > 1 ? v : 1);
+    } else {
+        long long v = (long long)w * max_dim / h;
+        *nw = (int)(v > 1 ? v : 1);
+        *nh = max_dim;
+    }
+}
+
+template <int LAYOUT>
+int launch_luma(rh_ctx *ctx, bool down2, const uint8_t *px, size_t row_pitch, size_t img_pitch, int n, int W, int H,
+                uint8_t *L) {
+    const size_t total = (size_t)n * W * H;
+    if (down2)
+        luma_plane_kernel<LAYOUT, true><<<cdiv(total, 256), 256, 0, ctx->stream>>>(px, row_pitch, img_pitch, n, W, H, L);
+    else
+        luma_plane_kernel<LAYOUT, false><<<cdiv(total, 256), 256, 0, ctx->stream>>>(px, row_pitch, img_pitch, n, W, H, L);
+    RH_LAUNCHED(ctx, "luma_plane_kernel");
+    return RH_OK;
+}
+
+// generic pipeline over one chunk of device-resident images
+int generic_chunk(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int n, int W, int H, size_t row_pitch,
+                  size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct) {
+    cudaStream_t st = ctx->stream;
+    const size_t plane = (size_t)W * H;
+    void *p;
+    RH_TRY(scratch(ctx, S_W0, plane * n, &p));
+    uint8_t *L = (uint8_t *)p;
+    RH_TRY(scratch(ctx, S_W1, plane * n * sizeof(float), &p));
+    float *A = (float *)p;
+    RH_TRY(scratch(ctx, S_W2, plane * n * sizeof(float), &p));
+    float *B = (float *)p;
+    if (layout == RH_LAYOUT_RGB8)
+        RH_TRY(launch_luma<RH_LAYOUT_RGB8>(ctx, down2, d_px, row_pitch, img_pitch, n, W, H, L));
+    else if (layout == RH_LAYOUT_RGBA8)
+        RH_TRY(launch_luma<RH_LAYOUT_RGBA8>(ctx, down2, d_px, row_pitch, img_pitch, n, W, H, L));
+    else
+        RH_TRY(launch_luma<RH_LAYOUT_LUMA8>(ctx, down2, d_px, row_pitch, img_pitch, n, W, H, L));
+    const int w_rows = (W + 63) / 64, w_cols = (H + 63) / 64;  // pdqhash.rs:246-247
+    // rep 1 (pdqhash.rs:422-425): rows L -> A, cols A -> B; rep 2: rows B -> A, cols A -> B
+    box_pass_kernel<uint8_t><<<cdiv((size_t)n * H, 128), 128, 0, st>>>(L, A, n, H, W, W, 1, plane, w_rows);
+    RH_LAUNCHED(ctx, "box_pass_kernel");
+    box_pass_kernel<float><<<cdiv((size_t)n * W, 128), 128, 0, st>>>(A, B, n, W, H, 1, W, plane, w_cols);
+    RH_LAUNCHED(ctx, "box_pass_kernel");
+    box_pass_kernel<float><<<cdiv((size_t)n * H, 128), 128, 0, st>>>(B, A, n, H, W, W, 1, plane, w_rows);
+    RH_LAUNCHED(ctx, "box_pass_kernel");
+    box_pass_kernel<float><<<cdiv((size_t)n * W, 128), 128, 0, st>>>(A, B, n, W, H, 1, W, plane, w_cols);
+    RH_LAUNCHED(ctx, "box_pass_kernel");
+    pdq_tail_kernel<SRC_PLANE><<<n, TAIL_THREADS, 0, st>>>(B, W, H, d_dct, out, out_offset);
+    RH_LAUNCHED(ctx, "pdq_tail_kernel");
+    return RH_OK;
+}
+
+__global__ void fill_u8_kernel(uint8_t *p, size_t n, uint8_t v) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h, size_t row_pitch,
+                      size_t img_pitch, uint8_t *out_hash, float *out_quality, float *out_coeffs,
+                      uint8_t *out_dihedral, uint8_t *out_valid) {
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || w <= 0 || h <= 0 || (n > 0 && !pixels)) return fail(ctx, RH_EINVAL, "rh_pdq_hash_batch: bad arguments");
+    if (layout != RH_LAYOUT_RGB8 && layout != RH_LAYOUT_RGBA8 && layout != RH_LAYOUT_LUMA8)
+        return fail(ctx, RH_EINVAL, "rh_pdq_hash_batch: unknown layout");
+    const int ch = layout == RH_LAYOUT_RGB8 ? 3 : (layout == RH_LAYOUT_RGBA8 ? 4 : 1);
+    if (row_pitch == 0) row_pitch = (size_t)w * ch;
+    if (img_pitch == 0) img_pitch = row_pitch * h;
+    if (row_pitch < (size_t)w * ch || img_pitch < row_pitch * (size_t)(h - 1) + (size_t)w * ch)
+        return fail(ctx, RH_EINVAL, "rh_pdq_hash_batch: pitch smaller than the image");
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->last_ms = 0.0;
+    ctx->last_units = 0.0;
+    if (n == 0) return RH_OK;
+
+    OutBuf<uint8_t> o_hash, o_dih, o_valid;
+    OutBuf<float> o_q, o_c;
+    RH_TRY(o_hash.prepare(ctx, out_hash, (size_t)n * 32, S_OUT0));
+    RH_TRY(o_q.prepare(ctx, out_quality, (size_t)n, S_OUT1));
+    RH_TRY(o_c.prepare(ctx, out_coeffs, (size_t)n * 256, S_OUT2));
+    RH_TRY(o_dih.prepare(ctx, out_dihedral, (size_t)n * 256, S_OUT3));
+    RH_TRY(o_valid.prepare(ctx, out_valid, (size_t)n, S_OUT4));
+
+    if (w < 5 || h < 5) {  // pdqhash.rs:167-169 -> None for every image of the batch
+        if (o_valid.dev) RH_CUDA(ctx, cudaMemsetAsync(o_valid.dev, 0, (size_t)n, st));
+        if (o_hash.dev) RH_CUDA(ctx, cudaMemsetAsync(o_hash.dev, 0, (size_t)n * 32, st));
+        if (o_q.dev) RH_CUDA(ctx, cudaMemsetAsync(o_q.dev, 0, (size_t)n * 4, st));
+        if (o_c.dev) RH_CUDA(ctx, cudaMemsetAsync(o_c.dev, 0, (size_t)n * 1024, st));
+        if (o_dih.dev) RH_CUDA(ctx, cudaMemsetAsync(o_dih.dev, 0, (size_t)n * 256, st));
+        RH_TRY(o_valid.finish(ctx));
+        RH_TRY(o_hash.finish(ctx));
+        RH_TRY(o_q.finish(ctx));
+        RH_TRY(o_c.finish(ctx));
+        RH_TRY(o_dih.finish(ctx));
+        RH_CUDA(ctx, cudaStreamSynchronize(st));
+        return RH_OK;
+    }
+
+    int W = w, H = h;
+    bool down2 = false;
+    if (w > 512 || h > 512) {  // pdqhash.rs:181-188
+        target_dimensions(w, h, 512, &W, &H);
+        if (W * 2 == w && H * 2 == h)
+            down2 = true;
+        else
+            return fail(ctx, RH_EUNSUPPORTED,
+                        "rh_pdq_hash_batch: pre-downsample ratio other than exactly 2x is not implemented");
+    }
+    const float *d_dct;
+    RH_TRY(ensure_dct(ctx, &d_dct));
+    TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
+    const bool fused = pdq_fused_supported(W, H) != 0;
+
+    const bool on_device = is_device_ptr(pixels);
+    // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
+    // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
+    int64_t chunk = fused ? 2048 : 256;
+    const size_t in_bytes_per = img_pitch;
+    if (!on_device) {
+        const size_t budget = size_t(512) << 20;
+        int64_t c2 = (int64_t)(budget / in_bytes_per);
+        if (c2 < 1) c2 = 1;
+        if (chunk > c2) chunk = c2;
+    }
+    if (chunk > n) chunk = n;
+
+    uint8_t *stage[2] = {nullptr, nullptr};
+    if (!on_device) {
+        void *p;
+        RH_TRY(scratch(ctx, S_IN0, (size_t)chunk * in_bytes_per, &p));
+        stage[0] = (uint8_t *)p;
+        RH_TRY(scratch(ctx, S_IN1, (size_t)chunk * in_bytes_per, &p));
+        stage[1] = (uint8_t *)p;
+    }
+    RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    int64_t k = 0;
+    for (int64_t off = 0; off < n; off += chunk, k++) {
+        const int64_t cn = (n - off < chunk) ? (n - off) : chunk;
+        const uint8_t *d_px = pixels + (size_t)off * img_pitch;
+        if (!on_device) {
+            const int b = (int)(k & 1);
+            // the staging buffer may be overwritten only once the kernels of chunk k-2 are done
+            if (k >= 2) RH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+            size_t bytes = (size_t)(cn - 1) * img_pitch + row_pitch * (size_t)(h - 1) + (size_t)w * ch;
+            RH_CUDA(ctx, cudaMemcpyAsync(stage[b], d_px, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            RH_CUDA(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+            RH_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
+            d_px = stage[b];
+        }
+        if (fused)
+            RH_TRY(pdq_fused_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
+        else
+            RH_TRY(generic_chunk(ctx, d_px, layout, down2, (int)cn, W, H, row_pitch, img_pitch, out, off, d_dct));
+        if (!on_device) RH_CUDA(ctx, cudaEventRecord(ctx->ev_done[k & 1], st));
+    }
+    RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    if (o_valid.dev) {
+        fill_u8_kernel<<<cdiv(n, 256), 256, 0, st>>>(o_valid.dev, (size_t)n, 1);
+        RH_LAUNCHED(ctx, "fill_u8_kernel");
+    }
+    RH_TRY(o_hash.finish(ctx));
+    RH_TRY(o_q.finish(ctx));
+    RH_TRY(o_c.finish(ctx));
+    RH_TRY(o_dih.finish(ctx));
+    RH_TRY(o_valid.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->last_ms = ms;
+    ctx->last_units = (double)n;
+    return RH_OK;
+}
+
+int rh_pdq_from_buffer64(rh_ctx *ctx, const float *buf64x64, int64_t n, uint8_t *out_hash, float *out_quality,
+                         float *out_coeffs, uint8_t *out_dihedral) {
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || (n > 0 && !buf64x64)) return fail(ctx, RH_EINVAL, "rh_pdq_from_buffer64: bad arguments");
+    if (n == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const float *d_in;
+    RH_TRY(stage_in(ctx, buf64x64, (size_t)n * 4096, S_IN0, &d_in));
+    OutBuf<uint8_t> o_hash, o_dih;
+    OutBuf<float> o_q, o_c;
+    RH_TRY(o_hash.prepare(ctx, out_hash, (size_t)n * 32, S_OUT0));
+    RH_TRY(o_q.prepare(ctx, out_quality, (size_t)n, S_OUT1));
+    RH_TRY(o_c.prepare(ctx, out_coeffs, (size_t)n * 256, S_OUT2));
+    RH_TRY(o_dih.prepare(ctx, out_dihedral, (size_t)n * 256, S_OUT3));
+    const float *d_dct;
+    RH_TRY(ensure_dct(ctx, &d_dct));
+    TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
+    pdq_tail_kernel<SRC_BUF64><<<(unsigned)n, TAIL_THREADS, 0, st>>>(d_in, 64, 64, d_dct, out, 0);
+    RH_LAUNCHED(ctx, "pdq_tail_kernel");
+    RH_TRY(o_hash.finish(ctx));
+    RH_TRY(o_q.finish(ctx));
+    RH_TRY(o_c.finish(ctx));
+    RH_TRY(o_dih.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    return RH_OK;
+}
+
+static int from_coeffs(rh_ctx *ctx, const float *coeffs, int64_t n, uint8_t *out_hash, uint8_t *out_dihedral) {
+    if (!ctx) return RH_EINVAL;
+    if (n < 0 || (n > 0 && !coeffs)) return fail(ctx, RH_EINVAL, "from_coeffs: bad arguments");
+    if (n == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const float *d_in;
+    RH_TRY(stage_in(ctx, coeffs, (size_t)n * 256, S_IN0, &d_in));
+    OutBuf<uint8_t> o_hash, o_dih;
+    RH_TRY(o_hash.prepare(ctx, out_hash, (size_t)n * 32, S_OUT0));
+    RH_TRY(o_dih.prepare(ctx, out_dihedral, (size_t)n * 256, S_OUT3));
+    TailOut out{o_hash.dev, nullptr, nullptr, o_dih.dev};
+    pdq_tail_kernel<SRC_COEFFS><<<(unsigned)n, TAIL_THREADS, 0, st>>>(d_in, 0, 0, nullptr, out, 0);
+    RH_LAUNCHED(ctx, "pdq_tail_kernel");
+    RH_TRY(o_hash.finish(ctx));
+    RH_TRY(o_dih.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    return RH_OK;
+}
+
+int rh_pdq_hash_from_coeffs(rh_ctx *ctx, const float *coeffs, int64_t n, uint8_t *out_hash) {
+    return from_coeffs(ctx, coeffs, n, out_hash, nullptr);
+}
+
+int rh_pdq_dihedral_from_coeffs(rh_ctx *ctx, const float *coeffs, int64_t n, uint8_t *out_dihedral) {
+    return from_coeffs(ctx, coeffs, n, nullptr, out_dihedral);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""Host mirror of the grouping core and feeder of src/scanner.rs over the CUDA library.
+
+    quality_100 / is_low_confidence   scanner.rs:1416-1418, :1588-1594
+    group_files_generic               scanner.rs:1640-1817 (edge phase + union-find -> groups)
+    group_with_pdqhash                scanner.rs:1827-1832
+    group_files_sharded               the same search tiled over the ranks of a process group
+    hash_files_batched                the scanner.rs:1202-1521 hash loop restructured into batches
+
+Groups are returned in the canonical form of SURVEY.md 8a: members ascending, groups ordered
+by first member (the reference's HashMap order is nondeterministic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import pdqhash
+from ._lib import MAX_SIMILARITY_256, PDQ_MIN_QUALITY, default_context, is_torch_tensor, lib, ptr
+
+
+def quality_100(q: float) -> int:
+    """scanner.rs:1416-1418: (q * 100).round().clamp(0, 100) as u16 (round half away from zero)."""
+    v = np.float32(q) * np.float32(100.0)
+    r = math.floor(float(v) + 0.5) if v >= 0 else -math.floor(-float(v) + 0.5)
+    return int(min(100, max(0, r)))
+
+
+def is_low_confidence(quality100) -> bool:
+    """scanner.rs:1588-1594 / :1631-1636: unknown quality counts as good."""
+    return quality100 is not None and quality100 < PDQ_MIN_QUALITY
+
+
+def labels_to_groups(labels) -> list:
+    """labels[i] = smallest index of i's component -> groups with > 1 member (scanner.rs:1809-1817)."""
+    labels = np.asarray(labels.cpu().numpy() if is_torch_tensor(labels) else labels).astype(np.int64)
+    order = np.argsort(labels, kind="stable")
+    sl = labels[order]
+    cut = np.flatnonzero(np.diff(sl)) + 1
+    groups = []
+    for part in np.split(order, cut):
+        if part.size > 1:
+            groups.append(part.tolist())
+    groups.sort(key=lambda g: g[0])
+    return groups
+
+
+def _u8(x):
+    if x is None or is_torch_tensor(x):
+        return x
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def _labels_out(like, n):
+    if is_torch_tensor(like) and like.is_cuda:
+        import torch
+        return torch.empty(n, dtype=torch.int32, device=like.device)
+    return np.empty(n, np.uint32)
+
+
+def group_labels(hashes, similarity, has_hash=None, variants=None, n_variants=None, low_conf=None, ctx=None):
+    """-> (labels[n], comparison_count).  similarity > 63 raises ValueError (scanner.rs:1650-1655)."""
+    ctx = ctx or default_context()
+    hashes = _u8(hashes)
+    n = int(hashes.shape[0])
+    labels = _labels_out(hashes, n)
+    cnt = C.c_uint64()
+    ctx.check(lib().rh_hamming_group(ctx.handle, ptr(hashes), ptr(_u8(has_hash)), ptr(_u8(variants)),
+                                     ptr(_u8(n_variants)), ptr(_u8(low_conf)), n, int(similarity), ptr(labels),
+                                     C.byref(cnt)))
+    return labels, int(cnt.value)
+
+
+def group_files_generic(hashes, similarity, has_hash=None, variants=None, n_variants=None, low_conf=None, ctx=None):
+    """scanner.rs:1640-1817 -> (groups, comparison_count)."""
+    labels, cnt = group_labels(hashes, similarity, has_hash, variants, n_variants, low_conf, ctx)
+    return labels_to_groups(labels), cnt
+
+
+def group_with_pdqhash(hashes, similarity, coefficients=None, quality100=None, has_hash=None, ctx=None):
+    """scanner.rs:1827-1832 with PdqStrategy (scanner.rs:1611-1637): files that carry cached
+    coefficients query with their 8 dihedral variants, the others with their own hash; a file
+    whose quality_100 < 50 is low-confidence."""
+    ctx = ctx or default_context()
+    variants = None
+    if coefficients is not None:
+        variants = pdqhash.dihedral_from_coeffs(coefficients, ctx)
+    low_conf = None
+    if quality100 is not None:
+        q = np.asarray(quality100)
+        low_conf = (q < PDQ_MIN_QUALITY).astype(np.uint8)
+    return group_files_generic(hashes, similarity, has_hash=has_hash, variants=variants, low_conf=low_conf, ctx=ctx)
+
+
+def edges(hashes, similarity, has_hash=None, variants=None, n_variants=None, low_conf=None, cap=1 << 20, ctx=None):
+    """Debug view: the (unordered) edge list of the same search -> (edges[k, 2], comparison_count)."""
+    ctx = ctx or default_context()
+    hashes = _u8(hashes)
+    n = int(hashes.shape[0])
+    out = np.zeros((cap, 2), np.uint32)
+    cnt = C.c_uint64()
+    ctx.check(lib().rh_hamming_edges(ctx.handle, ptr(hashes), ptr(_u8(has_hash)), ptr(_u8(variants)),
+                                     ptr(_u8(n_variants)), ptr(_u8(low_conf)), n, int(similarity), ptr(out), cap,
+                                     C.byref(cnt)))
+    return out[: min(cap, cnt.value)], int(cnt.value)
+
+
+def group_shard(hashes, similarity, rank, world, has_hash=None, variants=None, n_variants=None, low_conf=None,
+                ctx=None):
+    """One rank's tiles -> (local forest parent[n], local edge count)."""
+    ctx = ctx or default_context()
+    hashes = _u8(hashes)
+    n = int(hashes.shape[0])
+    parent = _labels_out(hashes, n)
+    cnt = C.c_uint64()
+    ctx.check(lib().rh_hamming_group_shard(ctx.handle, ptr(hashes), ptr(_u8(has_hash)), ptr(_u8(variants)),
+                                           ptr(_u8(n_variants)), ptr(_u8(low_conf)), n, int(similarity), int(rank),
+                                           int(world), ptr(parent), C.byref(cnt)))
+    return parent, int(cnt.value)
+
+
+def merge_forests(parents, ctx=None):
+    """(world, n) forests -> canonical labels[n] (rh_uf_merge)."""
+    ctx = ctx or default_context()
+    world, n = int(parents.shape[0]), int(parents.shape[1])
+    if not is_torch_tensor(parents):
+        parents = np.ascontiguousarray(parents, dtype=np.uint32)
+    labels = _labels_out(parents, n)
+    ctx.check(lib().rh_uf_merge(ctx.handle, ptr(parents), world, n, ptr(labels)))
+    return labels
+
+
+def group_files_sharded(hashes, similarity, group=None, has_hash=None, variants=None, n_variants=None, low_conf=None,
+                        ctx=None, shard_fn=None, merge_fn=None):
+    """The search tiled over the ranks of a torch.distributed process group (one process per
+    GPU): every rank scans its tiles, the n x u32 forests are all-gathered (NCCL over NVLink on
+    GPUs, gloo in the CPU tests), each rank merges them and the edge counts are all-reduced.
+    Labels are identical on every rank and to the single-GPU result.
+
+    shard_fn / merge_fn let the CPU (gloo) tests substitute the oracle's rank kernel for the
+    device calls; the product path never sets them.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    shard_fn = shard_fn or (lambda: group_shard(hashes, similarity, rank, world, has_hash, variants, n_variants,
+                                                low_conf, ctx))
+    parent, cnt = shard_fn()
+    if is_torch_tensor(parent):
+        local = parent
+    else:
+        local = torch.from_numpy(np.ascontiguousarray(parent).view(np.int32))
+    local = local.contiguous()
+    gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(gathered, local, group=group)   # NCCL: one n x u32 block per rank
+    else:
+        dist.all_gather(list(gathered.unbind(0)), local, group=group)
+    total = torch.tensor([cnt], dtype=torch.int64, device=local.device)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    if merge_fn is not None:
+        labels = merge_fn(gathered.cpu().numpy().view(np.uint32))
+    elif gathered.is_cuda:
+        labels = merge_forests(gathered, ctx)
+    else:
+        labels = merge_forests(gathered.numpy().view(np.uint32), ctx)
+    return labels, int(total.item())
+
+
+def hash_files_batched(images_iter, batch_size=256, want_coeffs=True, ctx=None, progress=None):
+    """Scanner-style feeder (scanner.rs:1202-1521 restructured): decoded images of mixed sizes
+    arrive one by one (the decode stays on the host, as in the reference); same-sized images
+    are collected into batches of `batch_size`, hashed on the device, and handed back in arrival
+    order as dicts(hash, quality, quality_100, coeffs) -- or None where the reference returns
+    None (scanner.rs:1481-1487 keeps the file without a hash)."""
+    ctx = ctx or default_context()
+    results = {}
+    pending = {}
+    total = 0
+
+    def flush(key):
+        idxs, imgs = pending.pop(key)
+        out = pdqhash.hash_batch(np.stack(imgs), want_coeffs=want_coeffs, ctx=ctx)
+        for k, i in enumerate(idxs):
+            if not out["valid"][k]:
+                results[i] = None
+                continue
+            q = float(out["quality"][k])
+            results[i] = {"hash": out["hash"][k].copy(), "quality": q, "quality_100": quality_100(q),
+                          "coeffs": out["coeffs"][k].copy() if want_coeffs else None}
+        if progress:
+            progress(len(results), total)
+
+    for i, img in enumerate(images_iter):
+        total = i + 1
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        if w < pdqhash.MIN_HASHABLE_DIM or h < pdqhash.MIN_HASHABLE_DIM:
+            results[i] = None
+            continue
+        key = img.shape
+        slot = pending.setdefault(key, ([], []))
+        slot[0].append(i)
+        slot[1].append(img)
+        if len(slot[0]) >= batch_size:
+            flush(key)
+    for key in list(pending):
+        flush(key)
+    return [results[i] for i in range(total)]

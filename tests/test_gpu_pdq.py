@@ -1,0 +1,222 @@
+"""GPU parity tests of hot path #1 (PDQ hashing) through the C ABI against the CPU oracle on
+the same pixels.  north_star tolerance: hash bits identical for >= 99.9 % of images, any
+mismatch within Hamming distance 2, quality within 1e-4 relative -- the device path is held to
+the stricter bar of bit-exact hashes, coefficients and quality, which implies it."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from rupphash_b200.synth import synth_images
+
+pytestmark = pytest.mark.gpu
+
+HASH_IDENTICAL_MIN_FRACTION = 0.999   # north_star
+HASH_MAX_MISMATCH_BITS = 2            # north_star
+QUALITY_REL_TOL = 1e-4                # north_star
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rupphash_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def lcg_buffer(seed):
+    """pdqhash.rs:606-614"""
+    state = seed & 0xFFFFFFFF
+    buf = np.zeros((64, 64), np.float32)
+    for r in range(64):
+        for c in range(64):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            buf[r, c] = np.float32((state >> 16) & 0xFF)
+    return buf
+
+
+def check_tolerance(got, want):
+    """the north_star rule, stated explicitly"""
+    n = len(want["hash"])
+    dist = np.unpackbits(np.bitwise_xor(got["hash"], want["hash"]), axis=1).sum(axis=1)
+    assert (dist == 0).mean() >= HASH_IDENTICAL_MIN_FRACTION or n < 1000 and (dist == 0).all()
+    assert dist.max() <= HASH_MAX_MISMATCH_BITS
+    rel = np.abs(got["quality"] - want["quality"]) / np.maximum(np.abs(want["quality"]), 1e-12)
+    assert rel.max() <= QUALITY_REL_TOL
+
+
+def check_exact(got, want):
+    assert np.array_equal(got["valid"], want["valid"])
+    assert np.array_equal(got["hash"], want["hash"])
+    assert np.array_equal(got["quality"], want["quality"])
+    if want.get("coeffs") is not None:
+        assert np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32)), "coefficient bits differ"
+    if want.get("dihedral") is not None:
+        assert np.array_equal(got["dihedral"], want["dihedral"])
+
+
+def test_tail_on_reference_lcg_buffers(ctx, orc):
+    """The 64x64 -> hash tail on the reference's own test inputs (pdqhash.rs:582-628)."""
+    from rupphash_b200 import pdqhash
+    rng = np.random.default_rng(0)
+    bufs = [lcg_buffer(s) for s in (1, 42, 0x12345678, 0xDEADBEEF, 7)]
+    bufs += [rng.random((64, 64), dtype=np.float32) * 255 for _ in range(20)]
+    bufs += [np.full((64, 64), 17.0, np.float32), np.zeros((64, 64), np.float32)]
+    bufs = np.stack(bufs)
+    got = pdqhash.from_buffer64(bufs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    for k in range(len(bufs)):
+        coeffs = orc.dct64_to_16(bufs[k])
+        assert np.array_equal(got["coeffs"][k].view(np.uint32), coeffs.view(np.uint32)), k
+        assert np.float32(orc.quality(bufs[k])) == got["quality"][k]
+        assert np.array_equal(got["hash"][k], orc.to_hash(coeffs))
+        assert np.array_equal(got["dihedral"][k], orc.dihedral(coeffs))
+
+
+def test_hash_and_dihedral_from_coeffs(ctx, orc):
+    from rupphash_b200 import pdqhash
+    rng = np.random.default_rng(1)
+    coeffs = (rng.standard_normal((300, 256)) * 40).astype(np.float32)
+    coeffs[0] = 0.0                      # all ties
+    coeffs[1, :128] = 5.0; coeffs[1, 128:] = -5.0
+    coeffs[2] = np.where(np.arange(256) % 2 == 0, 0.0, -0.0).astype(np.float32)  # +0 / -0 under total_cmp
+    coeffs[3, 7] = np.inf; coeffs[3, 9] = -np.inf
+    h = pdqhash.hash_from_coeffs(coeffs, ctx)
+    d = pdqhash.dihedral_from_coeffs(coeffs, ctx)
+    for k in range(len(coeffs)):
+        assert np.array_equal(h[k], orc.to_hash(coeffs[k])), k
+        assert np.array_equal(d[k], orc.dihedral(coeffs[k])), k
+    f = pdqhash.PdqFeatures(coeffs[10], ctx)
+    assert np.array_equal(f.to_hash(), orc.to_hash(coeffs[10]))
+    assert np.array_equal(f.generate_dihedral_hashes(), orc.dihedral(coeffs[10]))
+
+
+@pytest.mark.parametrize("shape", [(768, 1024, 3), (512, 512, 3), (384, 512, 3), (384, 512, 4), (384, 512),
+                                   (64, 64, 3), (5, 5, 3), (37, 5, 3), (300, 100, 3), (257, 511, 3), (100, 449, 3),
+                                   (720, 1024, 3), (1024, 640, 4), (480, 500)])
+def test_hash_batch_bit_exact(ctx, orc, shape):
+    from rupphash_b200 import pdqhash
+    h, w = shape[:2]
+    ch = shape[2] if len(shape) == 3 else 1
+    n = 6 if h * w > 400_000 else 12
+    imgs = synth_images(n, h, w, seed=h * 7 + w, channels=ch)
+    if ch == 1:
+        imgs = imgs[..., 0]
+    layout = {3: 0, 4: 1, 1: 2}[ch]
+    want = orc.pdq_batch(imgs if ch > 1 else imgs[..., None], layout=layout, threads=8, want_coeffs=True,
+                         want_dihedral=True)
+    got = pdqhash.hash_batch(imgs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    check_exact(got, want)
+    check_tolerance(got, want)
+
+
+def test_hash_batch_edge_content(ctx, orc):
+    """Flat, saturated, checkerboard and pure-noise images (low quality / tie-heavy medians)."""
+    from rupphash_b200 import pdqhash
+    rng = np.random.default_rng(3)
+    h, w = 384, 512
+    imgs = np.zeros((6, h, w, 3), np.uint8)
+    imgs[1] = 255
+    imgs[2] = ((np.add.outer(np.arange(h), np.arange(w)) & 1) * 255).astype(np.uint8)[..., None]
+    imgs[3] = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    imgs[4, :, : w // 2] = 200
+    imgs[5] = (np.arange(w) // 2 % 256).astype(np.uint8)[None, :, None]
+    want = orc.pdq_batch(imgs, threads=4, want_coeffs=True, want_dihedral=True)
+    got = pdqhash.hash_batch(imgs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    check_exact(got, want)
+    big = np.repeat(np.repeat(imgs, 2, axis=1), 2, axis=2)  # 768 x 1024 through the 2x pre-downsample
+    want = orc.pdq_batch(big, threads=4, want_coeffs=True)
+    got = pdqhash.hash_batch(big, want_coeffs=True, ctx=ctx)
+    check_exact(got, want)
+
+
+def test_too_small_is_none(ctx):
+    from rupphash_b200 import pdqhash
+    out = pdqhash.hash_batch(np.zeros((3, 4, 100, 3), np.uint8), ctx=ctx)
+    assert not out["valid"].any()
+    assert pdqhash.generate_pdq_features(np.zeros((100, 4, 3), np.uint8), ctx) is None
+    assert pdqhash.generate_pdq(np.zeros((4, 4), np.uint8), ctx) is None
+
+
+def test_unsupported_ratio_is_loud(ctx):
+    from rupphash_b200 import Unsupported, pdqhash
+    with pytest.raises(Unsupported):
+        pdqhash.hash_batch(np.zeros((1, 854, 1280, 3), np.uint8), ctx=ctx)
+
+
+def test_single_image_api(ctx, orc):
+    from rupphash_b200 import pdqhash
+    img = synth_images(1, 384, 512, seed=99)[0]
+    feats, q = pdqhash.generate_pdq_features(img, ctx)
+    coeffs, oq, _ = orc.pdq_features(img)
+    assert np.array_equal(feats.coefficients, coeffs) and q == oq
+    hsh, q2 = pdqhash.generate_pdq(img, ctx)
+    assert np.array_equal(hsh, orc.to_hash(coeffs)) and q2 == oq
+
+
+def test_device_resident_and_large_batch(ctx, orc):
+    """Config-2 shape, device-resident input, more images than one internal chunk."""
+    import torch
+    from rupphash_b200 import pdqhash
+    pool = synth_images(24, 768, 1024, seed=2024)
+    idx = np.arange(300) % len(pool)
+    d = torch.from_numpy(pool).cuda()[torch.from_numpy(idx).cuda()].contiguous()
+    got = pdqhash.hash_batch(d, want_coeffs=True, ctx=ctx)
+    assert got["hash"].is_cuda
+    want = orc.pdq_batch(pool, threads=8, want_coeffs=True)
+    assert np.array_equal(got["hash"].cpu().numpy(), want["hash"][idx])
+    assert np.array_equal(got["quality"].cpu().numpy(), want["quality"][idx])
+    assert np.array_equal(got["coeffs"].cpu().numpy(), want["coeffs"][idx])
+
+
+def test_parity_subset_2000_images(ctx, orc):
+    """SURVEY 8d config 2 parity subset: 2000 synthetic 1024x768 images, north_star tolerance
+    (and in fact bit-exact)."""
+    from rupphash_b200 import pdqhash
+    n, per = 2000, 250
+    exact = 0
+    for s in range(0, n, per):
+        imgs = synth_images(per, 768, 1024, seed=0xB200 + s)
+        want = orc.pdq_batch(imgs, threads=os.cpu_count() or 8)
+        got = pdqhash.hash_batch(imgs, ctx=ctx)
+        check_tolerance(got, want)
+        exact += int((got["hash"] == want["hash"]).all(axis=1).sum())
+        assert np.array_equal(got["quality"], want["quality"])
+    assert exact == n
+
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures(ctx, path):
+    """The committed golden vectors of the reference's JPEG fixtures (self-generated by the
+    oracle, tools/make_golden.py), hashed on the device."""
+    from rupphash_b200 import pdqhash
+    g = np.load(path)
+    got = pdqhash.hash_batch(g["luma512"][None], want_coeffs=True, want_dihedral=True, ctx=ctx)
+    assert np.array_equal(got["hash"][0], g["hash"])
+    assert got["quality"][0] == g["quality"]
+    assert np.array_equal(got["coeffs"][0], g["coeffs"])
+    assert np.array_equal(got["dihedral"][0], g["dihedral"])
+    if "crop_rgb" in g:
+        got = pdqhash.hash_batch(g["crop_rgb"][None], want_coeffs=True, want_dihedral=True, ctx=ctx)
+        assert np.array_equal(got["hash"][0], g["crop_hash"])
+        assert got["quality"][0] == g["crop_quality"]
+        assert np.array_equal(got["coeffs"][0], g["crop_coeffs"])
+        assert np.array_equal(got["dihedral"][0], g["crop_dihedral"])
+
+
+def test_dihedral_robustness_like_reference(ctx):
+    """hamminghash.rs:416-481 on the bench.jpg crop: each pixel-domain dihedral transform hashes to
+    within 22 bits of some variant of the original."""
+    from rupphash_b200 import hamminghash, pdqhash
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bench.npz"))
+    img = g["crop_rgb"]  # 768 x 1024: stays exactly 2x-reducible when rotated to 1024 x 768
+    variants = pdqhash.hash_batch(img[None], want_dihedral=True, ctx=ctx)["dihedral"][0]
+    transforms = [img, np.rot90(img, -1), np.rot90(img, 2), np.rot90(img, 1), img[:, ::-1], img[::-1],
+                  np.rot90(img, -1)[:, ::-1], np.rot90(img, -1)[::-1]]
+    for t in transforms:
+        hsh = pdqhash.hash_batch(np.ascontiguousarray(t)[None], ctx=ctx)["hash"][0]
+        d = hamminghash.hamming_distances(np.tile(hsh, (8, 1)), variants, ctx)
+        assert d.min() <= 22
