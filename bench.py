@@ -252,7 +252,8 @@ def main():
     e2e_value = world * Be * e2e_steps / e2e_wall
     h2d_bytes = Be * IMG_H * IMG_W * IMG_C
     d2h_bytes = Be * (32 + 4 + 1)
-    same = bool(np.array_equal(res["hash"], out_hash[:Be].cpu().numpy()))
+    pool_idx = np.concatenate([np.arange(min(hp, Be - s)) for s in range(0, Be, hp)])
+    same = bool(np.array_equal(res["hash"], out_hash.cpu().numpy()[pool_idx]))
 
     line = {
         "metric": "pdq_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,

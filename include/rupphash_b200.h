@@ -134,8 +134,9 @@ int rh_hamming_distances_u64(rh_ctx *ctx, const uint64_t *a, const uint64_t *b, 
  *   hashes      n x 32 bytes (file.pdqhash; rows without a hash are ignored)
  *   has_hash    n bytes or NULL (= all Some)                          scanner.rs:1658-1662
  *   variants    n x 8 x 32 bytes or NULL.  NULL: every file queries with its own hash
- *               (scanner.rs:1624-1627); else n_variants[i] (or 8 when n_variants is NULL)
- *               leading variants of file i are the queries (scanner.rs:1615-1623).
+ *               (scanner.rs:1624-1627); else the n_variants[i] leading variants of file i
+ *               (clamped to 1..8; 8 when n_variants is NULL) are its queries
+ *               (scanner.rs:1615-1623: a file always queries with at least one hash).
  *   low_conf    n bytes or NULL: is_low_confidence (scanner.rs:1631-1636); a pair with a
  *               low-confidence side only matches at distance 0 (scanner.rs:1699,1721)
  *   similarity  <= 63, else RH_EINVAL

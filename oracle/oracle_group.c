@@ -482,13 +482,13 @@ int orc_group_tiles_rank(const uint8_t *hashes, const uint8_t *has_hash, const u
     /* flatten queries */
     size_t nq = 0;
     for (size_t i = 0; i < n; i++)
-        if (!has_hash || has_hash[i]) nq += variants ? (n_variants ? n_variants[i] : 8) : 1;
+        if (!has_hash || has_hash[i]) nq += variants ? (n_variants ? (n_variants[i] < 1 ? 1 : (n_variants[i] > 8 ? 8 : n_variants[i])) : 8) : 1;
     uint32_t *qfile = (uint32_t *)malloc((nq + 1) * sizeof(uint32_t));
     const uint8_t **qhash = (const uint8_t **)malloc((nq + 1) * sizeof(uint8_t *));
     size_t q = 0;
     for (size_t i = 0; i < n; i++) {
         if (has_hash && !has_hash[i]) continue;
-        int cnt = variants ? (n_variants ? n_variants[i] : 8) : 1;
+        int cnt = variants ? (n_variants ? (n_variants[i] < 1 ? 1 : (n_variants[i] > 8 ? 8 : n_variants[i])) : 8) : 1;
         for (int v = 0; v < cnt; v++) {
             qfile[q] = (uint32_t)i;
             qhash[q] = variants ? variants + i * 256 + (size_t)v * 32 : hashes + i * 32;

@@ -189,7 +189,7 @@ __global__ void flags_kernel(const uint8_t *has_hash, const uint8_t *n_variants,
     uint32_t v = 0, q = 0;
     if (i < n) {
         v = has_hash ? (has_hash[i] != 0) : 1u;
-        if (v) q = has_variants ? (n_variants ? min((uint32_t)n_variants[i], 8u) : 8u) : 1u;
+        if (v) q = has_variants ? (n_variants ? min(max((uint32_t)n_variants[i], 1u), 8u) : 8u) : 1u;
     }
     valid[i] = v;
     nv[i] = q;
