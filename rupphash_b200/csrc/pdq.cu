@@ -8,12 +8,14 @@
 // Both end in pdq_tail.cuh.  Arithmetic is f32 with explicit round-to-nearest mul/add/div
 // intrinsics, so nvcc can never contract a*b+c into an FMA (Rust never does).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "pdq_tail.cuh"
 
 namespace rh {
 int pdq_fused_supported(int W, int H);
+int pdq_fused_aligned(const void *px, size_t row_pitch, size_t img_pitch);
 int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int64_t n, int W, int H, size_t row_pitch,
                   size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct);
 }  // namespace rh
@@ -295,9 +297,11 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
     const float *d_dct;
     RH_TRY(ensure_dct(ctx, &d_dct));
     TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
-    const bool fused = pdq_fused_supported(W, H) != 0;
-
     const bool on_device = is_device_ptr(pixels);
+    // host input is staged into 256-byte aligned buffers, so only the pitches matter there
+    const bool fused = pdq_fused_supported(W, H) != 0 &&
+                       pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) &&
+                       !getenv("RH_PDQ_FORCE_GENERIC");
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
     int64_t chunk = fused ? 2048 : 256;

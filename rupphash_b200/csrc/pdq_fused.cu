@@ -1,11 +1,521 @@
-// pdq_fused.cu -- placeholder until the fused front end lands.
+// pdq_fused.cu -- the bandwidth kernel of hot path #1: RGB8/RGBA8/Luma8 pixels -> luma601 ->
+// (2x Box pre-downsample) -> two Jarosz box-filter repetitions -> 64x64 decimation -> quality,
+// DCT, median, hash, in ONE persistent kernel for planes 512 px wide (both BASELINE shapes:
+// 1024x768 -> 512x384 and 512x512).  Replaces pdqhash.rs:166-262 for those shapes; every other
+// shape takes the generic pipeline in pdq.cu.  Results are bit-identical to the reference's
+// sequential float arithmetic (tools/fused_model.py proves the restructuring on the CPU).
+//
+// Why it is not four float passes.  With a row window of 8 (pdqhash.rs:246: ceil(512/64)):
+//   * pass 1 (rows) of u8 luma is exact -- P1 = H/8, H an integer <= 2040 -- except in the six
+//     columns 0,1,2,508,509,510 whose clipped windows divide by 5,6,7;
+//   * pass 2 (columns) of exact eighths has exact running sums, hence away from those columns
+//     P2[r][c] = RN(S2d / (8 cnt_r)) with S2d the integer 2-D box sum: integer work + 1 rounding;
+//   * passes 3 and 4 are true sequential float chains (rounding error persists along a line) and
+//     are run as written -- one thread per row / per column -- but pass 4 only needs the 64
+//     decimated columns of pass 3, so only those are kept (64 floats per row).
+// The six inexact columns get the reference's real column chain (one lane each).
+//
+// Data flow per image (one CTA, 256 threads, ~75 KB shared memory, 3 CTAs per SM):
+//   for each band of 128 rows:
+//     F  all warps : global (128-bit loads, each pixel read once + 4 % halo) -> luma -> 2x2 rounded
+//                    average -> u8 luma band in shared memory (the only copy of the plane)
+//     E  edge cols : P1 of the six inexact columns, then their sequential column chains
+//     C  5-6 warps : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
+//                    registers, vertical window sums come from warp shuffles, S2d -> float ->
+//                    FMA-corrected division -> pass-3 chain; 64 samples per row go to a per-CTA
+//                    L2-resident scratch (column-major, coalesced)
+//   T  pass 4 over the scratch (64 column chains), decimate, then pdq_tail.cuh.
+// HBM traffic is the pixels (read once) plus 36 B of results; the f32 planes of the reference
+// never exist.
 #include "common.cuh"
 #include "pdq_tail.cuh"
 
-namespace rh {
-int pdq_fused_supported(int, int) { return 0; }
-int pdq_fused_run(rh_ctx *ctx, const uint8_t *, int, bool, int64_t, int, int, size_t, size_t, const TailOut &, int64_t,
-                  const float *) {
-    return fail(ctx, RH_EUNSUPPORTED, "fused PDQ kernel not built");
+namespace {
+
+using namespace rh;
+
+constexpr int FW = 512;           // plane width served by this kernel
+constexpr int FLP = 528;          // luma row pitch in bytes: 512 + 16 zero bytes; 528 % 128 == 16
+                                  // keeps the per-row LDS.128 of 8 consecutive lanes conflict-free
+constexpr int FBAND = 128;        // output rows per band
+constexpr int FTHREADS = 256;
+constexpr int FMAXL = FBAND + 7;  // luma rows per band including the vertical halo (window <= 8)
+constexpr int P3_PITCH = 512;     // floats per column of the pass-3 scratch
+constexpr size_t FSMEM = (size_t)FMAXL * FLP + (size_t)FMAXL * 6 * 4 + 8 * 6 * 4;
+
+static_assert(sizeof(TailSmem) <= (size_t)FMAXL * FLP, "tail scratch must fit in the luma band");
+
+struct FusedArgs {
+    const uint8_t *px;
+    size_t row_pitch, img_pitch;
+    int64_t n;
+    int H;
+    float *p3t;        // [gridDim.x][64][P3_PITCH]
+    const float *dct;  // 16 x 64
+    TailOut out;
+    int64_t out_offset;
+};
+
+// ------------------------------------------------------------------ front end ----
+
+template <int BYTES>
+__device__ __forceinline__ void load_chunk(const uint8_t *p, uint32_t *w) {
+    if (BYTES % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; i++) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < BYTES / 8; i++) {
+            uint2 v = __ldg(reinterpret_cast<const uint2 *>(p) + i);
+            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+        }
+    }
 }
+
+// pdqhash.rs:268-284 for pixel k of a chunk held in words w[].  RGB pixels straddle words; every
+// alignment is two DP2A (16-bit weights x 8-bit samples) with no byte shuffling.
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t luma_px(const uint32_t *w, int k) {
+    constexpr uint32_t W_RG = 299u | (587u << 16), W_B0 = 114u, W_0R = 299u << 16, W_GB = 587u | (114u << 16);
+    if (LAYOUT == RH_LAYOUT_LUMA8) return (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+    uint32_t v;
+    if (LAYOUT == RH_LAYOUT_RGBA8) {
+        v = __dp2a_lo(W_RG, w[k], 500u);
+        v = __dp2a_hi(W_B0, w[k], v);
+    } else {
+        const int o = 3 * k, i = o >> 2, sh = o & 3;
+        if (sh == 0) {
+            v = __dp2a_lo(W_RG, w[i], 500u);
+            v = __dp2a_hi(W_B0, w[i], v);
+        } else if (sh == 1) {
+            v = __dp2a_lo(W_0R, w[i], 500u);
+            v = __dp2a_hi(W_GB, w[i], v);
+        } else if (sh == 2) {
+            v = __dp2a_hi(W_RG, w[i], 500u);
+            v = __dp2a_lo(W_B0, w[i + 1], v);
+        } else {
+            v = __dp2a_hi(W_0R, w[i], 500u);
+            v = __dp2a_lo(W_GB, w[i + 1], v);
+        }
+    }
+    return __umulhi(v, 4294968u);  // floor(v / 1000), exact for v < 6.1e6
+}
+
+// 8 consecutive luma pixels of one plane row from the thread's source chunk(s).
+template <int LAYOUT, bool DOWN2, int NW>
+__device__ __forceinline__ uint2 luma8(const uint32_t *w0, const uint32_t *w1) {
+    uint32_t l[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (DOWN2) {
+            // Box 2x: horizontal pass first, each pass rounds half up (pdqhash.rs:203-220)
+            const uint32_t h0 = (luma_px<LAYOUT>(w0, 2 * k) + luma_px<LAYOUT>(w0, 2 * k + 1) + 1u) >> 1;
+            const uint32_t h1 = (luma_px<LAYOUT>(w1, 2 * k) + luma_px<LAYOUT>(w1, 2 * k + 1) + 1u) >> 1;
+            l[k] = (h0 + h1 + 1u) >> 1;
+        } else {
+            l[k] = luma_px<LAYOUT>(w0, k);
+        }
+    }
+    uint2 r;
+    r.x = l[0] | (l[1] << 8) | (l[2] << 16) | (l[3] << 24);
+    r.y = l[4] | (l[5] << 8) | (l[6] << 16) | (l[7] << 24);
+    return r;
+}
+
+// Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
+// sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
+template <int LAYOUT, bool DOWN2>
+__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
+                                          uint8_t *sL) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    constexpr int SPP = DOWN2 ? 2 : 1;
+    constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
+    constexpr int NW = BYTES / 4;
+    const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+    const uint8_t *colp = src + (size_t)col8 * BYTES;
+    for (int s = rsub; s < nL; s += 8) {
+        uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1];
+        const int sA = s, sB = s + 4;
+        const int lrA = Lr0 + sA, lrB = Lr0 + sB;
+        const bool okA = lrA >= 0 && lrA < H;
+        const bool okB = sB < nL && lrB >= 0 && lrB < H;
+        if (okA) {
+            const uint8_t *p = colp + (size_t)(lrA * SPP) * row_pitch;
+            load_chunk<BYTES>(p, a0);
+            if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
+        }
+        if (okB) {
+            const uint8_t *p = colp + (size_t)(lrB * SPP) * row_pitch;
+            load_chunk<BYTES>(p, b0);
+            if (DOWN2) load_chunk<BYTES>(p + row_pitch, b1);
+        }
+        // rows outside the image are stored as zeros: the chain phase then needs no clipping
+        uint2 vA = make_uint2(0u, 0u), vB = make_uint2(0u, 0u);
+        if (okA) vA = luma8<LAYOUT, DOWN2, NW>(a0, a1);
+        if (okB) vB = luma8<LAYOUT, DOWN2, NW>(b0, b1);
+        *reinterpret_cast<uint2 *>(sL + (size_t)sA * FLP + col8 * 8) = vA;
+        if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)sA * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
+        if (sB < nL) {
+            *reinterpret_cast<uint2 *>(sL + (size_t)sB * FLP + col8 * 8) = vB;
+            if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)sB * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- edge columns ----
+
+// Phase E1: pass-1 values of the six columns whose clipped row window is 5, 6 or 7 wide
+// (box_one_d_float phases 2 and 4, pdqhash.rs:372-378, :389-395): rounded quotients.
+__device__ __forceinline__ void edge_p1(const uint8_t *sL, float *sE, int nL) {
+    for (int idx = threadIdx.x; idx < nL * 6; idx += FTHREADS) {
+        const int s = idx / 6, e = idx - 6 * s;
+        const int lo = e < 3 ? 0 : 502 + e;     // 505, 506, 507
+        const int hi = e < 3 ? 4 + e : 511;     // 4, 5, 6
+        const uint8_t *row = sL + (size_t)s * FLP;
+        int acc = 0;
+        for (int c = lo; c <= hi; c++) acc += row[c];
+        sE[idx] = __fdiv_rn((float)acc, (float)(hi - lo + 1));
+    }
+}
+
+struct EdgeState {
+    float sum, cnt;
+};
+
+// Phase E2: the column chain of one inexact column (lane = column), continued across bands and
+// written in terms of the OUTPUT row o (box_one_d_float, pdqhash.rs:341-396, window WC, length H):
+//   grow   o in [0, HT]          sum += in[o+HB]; cnt += 1
+//   slide  o in [HT+1, H-HALF]   sum += in[o+HB]; sum -= in[o-HT-1]
+//   shrink o in [H-HALF+1, H-1]  sum -= in[o-HT-1]; cnt -= 1
+// Inputs P1 come from sE[slot(row)]; outputs P2 overwrite sE[slot(o)] (slot(o) < slot(o+HB), that
+// input has been consumed and parked in the 8-row ring by then).
+template <int WC>
+__device__ __forceinline__ void edge_chain(EdgeState &st, float *sE, float *sRing, int lane, int H, int b0,
+                                           int rows_out, int Lr0) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+    for (int o = b0; o < b0 + rows_out; o++) {
+        if (o == 0) {  // pdqhash.rs:366-370: the leading half window, no output
+            for (int i = 0; i < HALF - 1; i++) {
+                const float x = sE[(i - Lr0) * 6 + lane];
+                st.sum = __fadd_rn(st.sum, x);
+                st.cnt += 1.0f;
+                sRing[(i & 7) * 6 + lane] = x;
+            }
+        }
+        const int rin = o + HB, rout = o - HT - 1;
+        if (o <= HT) {
+            const float x = sE[(rin - Lr0) * 6 + lane];
+            st.sum = __fadd_rn(st.sum, x);
+            st.cnt += 1.0f;
+            sRing[(rin & 7) * 6 + lane] = x;
+        } else if (o <= H - HALF) {
+            const float x = sE[(rin - Lr0) * 6 + lane];
+            const float old = sRing[(rout & 7) * 6 + lane];  // read before the slot is reused (WC == 8)
+            st.sum = __fadd_rn(st.sum, x);
+            st.sum = __fsub_rn(st.sum, old);
+            sRing[(rin & 7) * 6 + lane] = x;
+        } else {
+            const float old = sRing[(rout & 7) * 6 + lane];
+            st.sum = __fsub_rn(st.sum, old);
+            st.cnt -= 1.0f;
+        }
+        sE[(o - Lr0) * 6 + lane] = __fdiv_rn(st.sum, st.cnt);
+    }
+}
+
+// ------------------------------------------------------------------ chain phase ----
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
+// sum over WC consecutive lanes starting at this lane (packed u16x2 fields cannot overflow:
+// 8 rows x 2040 < 65536)
+template <int WC>
+__device__ __forceinline__ uint32_t window_sum_down(uint32_t h) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t a2 = h + __shfl_down_sync(FULL, h, 1);
+    if (WC == 2) return a2;
+    if (WC == 3) return a2 + __shfl_down_sync(FULL, h, 2);
+    const uint32_t a4 = a2 + __shfl_down_sync(FULL, a2, 2);
+    if (WC == 4) return a4;
+    if (WC == 5) return a4 + __shfl_down_sync(FULL, h, 4);
+    if (WC == 6) return a4 + __shfl_down_sync(FULL, a2, 4);
+    if (WC == 7) return a4 + __shfl_down_sync(FULL, a2, 4) + __shfl_down_sync(FULL, h, 6);
+    return a4 + __shfl_down_sync(FULL, a4, 4);
+}
+
+// RN(s / d) for the integer s held in a 16-bit field of `packed` (sel picks the field) and
+// d = 8 cnt (or 4 cnt), y = RN(1/d):  q = f y;  r = fma(-d, q, f);  q' = fma(r, y, q).
+// Equal to IEEE division for every (s <= 16320, cnt <= 8): tools/fused_model.py and
+// tests/test_fused_model.py check the whole set.
+__device__ __forceinline__ float div_exact(uint32_t packed, uint32_t sel, float d, float y) {
+    const float f = __fsub_rn(__uint_as_float(prmt(packed, 0x4B000000u, sel)), 8388608.0f);
+    const float q = __fmul_rn(f, y);
+    const float r = __fmaf_rn(-d, q, f);
+    return __fmaf_rn(r, y, q);
+}
+
+struct ChainState {
+    uint32_t aprev;   // previous even-aligned entering pair (L[e+2], L[e+3])
+    uint32_t Hp;      // (H[e-2], H[e-1]): horizontal clipped 8-sums, packed u16x2
+    uint32_t S[4];    // entering sums of the last four pair steps (an 8-column delay line)
+    float ring[8];    // P2 of the last 8 columns
+    float sum;        // pass-3 running sum
+};
+
+enum { G_FIRST = 0, G_MID = 1, G_LAST = 2 };
+
+// One 16-column group of the pass-3 row chain: entering columns e = 16 g - 4 .. 16 g + 11, two per
+// step.  `cur` holds luma columns 16 g .. 16 g + 15 of the lane's row.
+template <int WC, int KIND>
+__device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, float d8, float y8, float d4,
+                                            float y4, const float *p2e, float *p3col, bool store) {
+    const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        // entering bytes L[e+4], L[e+5] are bytes 2p, 2p+1 of this group
+        const uint32_t aeven = prmt(cw[p >> 1], 0u, (p & 1) ? 0x4342u : 0x4140u);
+        const uint32_t aodd = prmt(st.aprev, aeven, 0x5432u);  // (L[e+3], L[e+4])
+        st.aprev = aeven;
+        const uint32_t snew = aodd + aeven;
+        st.Hp = st.Hp + snew - st.S[p & 3];                    // -> (H[e], H[e+1])
+        st.S[p & 3] = snew;
+        if (KIND == G_FIRST && p < 2) continue;                // e < 0: only the sliding sums advance
+        if (KIND == G_LAST && p >= 2) continue;                // e > 511
+        const uint32_t b = window_sum_down<WC>(st.Hp);         // S2d of this lane's output row
+        float x0, x1;
+        if (KIND == G_FIRST && p == 2) {                       // e = 0, 1: inexact columns
+            x0 = p2e[0];
+            x1 = p2e[1];
+        } else if (KIND == G_FIRST && p == 3) {                // e = 2 inexact, e = 3 exact
+            x0 = p2e[2];
+            x1 = div_exact(b, 0x7632u, d8, y8);
+        } else if (KIND == G_LAST && p == 0) {                 // e = 508, 509
+            x0 = p2e[3];
+            x1 = p2e[4];
+        } else if (KIND == G_LAST && p == 1) {                 // e = 510 inexact; e = 511: 4-wide window
+            x0 = p2e[5];
+            x1 = div_exact(b, 0x7632u, d4, y4);
+        } else {
+            x0 = div_exact(b, 0x7610u, d8, y8);
+            x1 = div_exact(b, 0x7632u, d8, y8);
+        }
+        // pass-3 chain (pdqhash.rs:366-387): entering column e, leaving e - 8, output column e - 4
+        const bool full = !(KIND == G_FIRST && p < 6);         // e >= 8
+        const int k0 = (2 * p) & 7, k1 = (2 * p + 1) & 7;
+        st.sum = __fadd_rn(st.sum, x0);
+        if (full) st.sum = __fsub_rn(st.sum, st.ring[k0]);
+        st.ring[k0] = x0;
+        if (full && (p == 2 || p == 6) && KIND != G_LAST) {
+            // output column e - 4 = 8 j + 4 is decimation sample j (pdqhash.rs:439), j = (e - 8) / 8
+            const int j = 2 * g - (p == 2 ? 1 : 0);
+            if (store) __stcg(p3col + (size_t)j * P3_PITCH, __fmul_rn(st.sum, 0.125f));
+        }
+        st.sum = __fadd_rn(st.sum, x1);
+        if (full) st.sum = __fsub_rn(st.sum, st.ring[k1]);
+        st.ring[k1] = x1;
+    }
+}
+
+// Phase C for one band: lane = row.  Warp w owns luma slots [w OPW, w OPW + 31] of the band window
+// and produces output rows b0 + w OPW + lane for lane < OPW = 33 - WC.
+template <int WC>
+__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, float *p3t, int H, int b0,
+                                            int rows_out, int nL) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ro = warp * OPW + lane;   // output row within the band == luma slot of the window top
+    const int r = b0 + ro;
+    const bool store = lane < OPW && ro < rows_out;
+    const int lo = max(0, r - HT), hi = min(H - 1, r + HB);
+    const float cnt = (float)max(1, hi - lo + 1);   // rows in the clipped column window
+    const float d8 = 8.0f * cnt, d4 = 4.0f * cnt;
+    const float y8 = __frcp_rn(d8), y4 = __frcp_rn(d4);
+    const uint8_t *rowp = sL + (size_t)min(ro, nL - 1) * FLP;
+    const float *p2e = sE + min(ro + HT, nL - 1) * 6;
+    float *p3col = p3t + r;
+    ChainState st;
+    st.aprev = 0u;
+    st.Hp = 0u;
+    st.sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) st.S[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) st.ring[i] = 0.0f;
+    chain_group<WC, G_FIRST>(st, *reinterpret_cast<const uint4 *>(rowp), 0, d8, y8, d4, y4, p2e, p3col, store);
+#pragma unroll 1
+    for (int g = 1; g < 32; g++)
+        chain_group<WC, G_MID>(st, *reinterpret_cast<const uint4 *>(rowp + 16 * g), g, d8, y8, d4, y4, p2e, p3col, store);
+    chain_group<WC, G_LAST>(st, *reinterpret_cast<const uint4 *>(rowp + FW), 32, d8, y8, d4, y4, p2e, p3col, store);
+    // first output of the shrink phase: column 508 = sample 63, window of 7 (pdqhash.rs:389-395).
+    // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
+    st.sum = __fsub_rn(st.sum, st.ring[4]);
+    if (store) __stcg(p3col + (size_t)63 * P3_PITCH, __fdiv_rn(st.sum, 7.0f));
+}
+
+// ------------------------------------------------------------------------ tail ----
+
+// Pass 4 for decimated column j: the column chain over the pass-3 samples (window WC, length H),
+// keeping the 64 decimated rows (pdqhash.rs:435).
+template <int WC>
+__device__ __forceinline__ void pass4_column(const float *col, int H, float *B, int j) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+    float sum = 0.0f, cnt = 0.0f;
+    int i_next = 0, ini = H >> 7;   // ((2 i + 1) H) / 128 for i = 0
+    float prev[8], cur[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) prev[k] = 0.0f;
+    for (int r0 = 0; r0 < H; r0 += 8) {
+        const float4 v0 = __ldcg(reinterpret_cast<const float4 *>(col + r0));
+        const float4 v1 = __ldcg(reinterpret_cast<const float4 *>(col + r0 + 4));
+        cur[0] = v0.x; cur[1] = v0.y; cur[2] = v0.z; cur[3] = v0.w;
+        cur[4] = v1.x; cur[5] = v1.y; cur[6] = v1.z; cur[7] = v1.w;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ri = r0 + k;
+            if (ri >= H) break;
+            const float x = cur[k];
+            bool emit = true;
+            if (ri < HALF - 1) {
+                sum = __fadd_rn(sum, x);
+                cnt += 1.0f;
+                emit = false;
+            } else if (ri < WC) {
+                sum = __fadd_rn(sum, x);
+                cnt += 1.0f;
+            } else {
+                const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
+                sum = __fadd_rn(sum, x);
+                sum = __fsub_rn(sum, old);
+            }
+            if (emit && ri - HB == ini) {
+                B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
+                i_next++;
+                ini = ((2 * i_next + 1) * H) >> 7;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) prev[k] = cur[k];
+    }
+    // shrink phase: outputs H-HB .. H-1, leaving rows H-WC ..
+    for (int k = 0; k < HALF - 1; k++) {
+        const float old = __ldcg(col + (H - WC + k));
+        sum = __fsub_rn(sum, old);
+        cnt -= 1.0f;
+        if (H - HB + k == ini && i_next < 64) {
+            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
+            i_next++;
+            ini = ((2 * i_next + 1) * H) >> 7;
+        }
+    }
+    (void)HT;
+}
+
+template <int LAYOUT, bool DOWN2, int WC>
+__global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *sL = smem;
+    float *sE = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);
+    float *sRing = sE + FMAXL * 6;
+    TailSmem &ts = *reinterpret_cast<TailSmem *>(smem);   // aliases the luma band, used after the last band
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, OPW = 33 - WC;
+    constexpr int NWC = (FBAND + OPW - 1) / OPW;           // warps that run row chains
+    static_assert(NWC <= 7, "warp 7 is reserved for the edge columns");
+    const int H = a.H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *p3t = a.p3t + (size_t)blockIdx.x * 64 * P3_PITCH;
+
+    for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
+        const uint8_t *src = a.px + (size_t)img * a.img_pitch;
+        EdgeState est;
+        est.sum = 0.0f;
+        est.cnt = 0.0f;
+        for (int b0 = 0; b0 < H; b0 += FBAND) {
+            const int rows_out = min(FBAND, H - b0);
+            const int Lr0 = b0 - HT;
+            const int nL = rows_out + WC - 1;
+            front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL);
+            __syncthreads();
+            edge_p1(sL, sE, nL);
+            __syncthreads();
+            if (warp == 7 && lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
+            __syncthreads();
+            if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL);
+            __syncthreads();
+        }
+        // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
+        if (threadIdx.x < 64) pass4_column<WC>(p3t + (size_t)threadIdx.x * P3_PITCH, H, ts.B, threadIdx.x);
+        for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
+        __syncthreads();
+        const size_t oimg = (size_t)img + (size_t)a.out_offset;
+        const float q = tail_quality(ts);
+        if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
+        tail_dct(ts);
+        if (a.out.coeffs) a.out.coeffs[oimg * 256 + threadIdx.x] = ts.C[threadIdx.x];
+        tail_hashes(ts, a.out, oimg);
+        __syncthreads();   // the next image's front end overwrites the aliased tail scratch
+    }
+}
+
+template <int LAYOUT, bool DOWN2, int WC>
+int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
+    auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC>;
+    RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
+    kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
+    RH_LAUNCHED(ctx, "pdq_fused_kernel");
+    return RH_OK;
+}
+
+template <int LAYOUT, bool DOWN2>
+int dispatch_wc(rh_ctx *ctx, const FusedArgs &a, int grid, int wc) {
+    if (wc == 6) return launch_fused<LAYOUT, DOWN2, 6>(ctx, a, grid);
+    if (wc == 8) return launch_fused<LAYOUT, DOWN2, 8>(ctx, a, grid);
+    return fail(ctx, RH_EUNSUPPORTED, "fused PDQ kernel: column window not instantiated");
+}
+
+}  // namespace
+
+namespace rh {
+
+// planes 512 wide whose column window ceil(H / 64) is 6 or 8 (H in 321..384 or 449..512)
+int pdq_fused_supported(int W, int H) {
+    if (W != FW || H > 512) return 0;
+    const int wc = (H + 63) / 64;
+    return wc == 6 || wc == 8;
+}
+
+// 128-bit loads need 16-byte aligned rows
+int pdq_fused_aligned(const void *px, size_t row_pitch, size_t img_pitch) {
+    return ((reinterpret_cast<uintptr_t>(px) | row_pitch | img_pitch) & 15) == 0;
+}
+
+int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int64_t n, int W, int H, size_t row_pitch,
+                  size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct) {
+    if (!pdq_fused_supported(W, H)) return fail(ctx, RH_EUNSUPPORTED, "fused PDQ kernel: unsupported plane size");
+    if ((reinterpret_cast<uintptr_t>(d_px) | row_pitch | img_pitch) & 15)
+        return fail(ctx, RH_EINVAL, "fused PDQ kernel: pixels must be 16-byte aligned (pdq_fused_aligned)");
+    int grid = ctx->sm_count * 3;
+    if (grid > n) grid = (int)n;
+    void *p;
+    RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p));
+    FusedArgs a;
+    a.px = d_px;
+    a.row_pitch = row_pitch;
+    a.img_pitch = img_pitch;
+    a.n = n;
+    a.H = H;
+    a.p3t = (float *)p;
+    a.dct = d_dct;
+    a.out = out;
+    a.out_offset = out_offset;
+    const int wc = (H + 63) / 64;
+    if (layout == RH_LAYOUT_RGB8)
+        return down2 ? dispatch_wc<RH_LAYOUT_RGB8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGB8, false>(ctx, a, grid, wc);
+    if (layout == RH_LAYOUT_RGBA8)
+        return down2 ? dispatch_wc<RH_LAYOUT_RGBA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGBA8, false>(ctx, a, grid, wc);
+    return down2 ? dispatch_wc<RH_LAYOUT_LUMA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_LUMA8, false>(ctx, a, grid, wc);
+}
+
 }  // namespace rh

@@ -1,0 +1,60 @@
+"""CPU proofs behind the fused PDQ kernel (rupphash_b200/csrc/pdq_fused.cu):
+  * the FMA-corrected division it uses equals IEEE f32 division on the whole finite input set;
+  * the restructured algorithm (integer 2-D box sums + one rounding, real chains only where the
+    data is inexact) reproduces the oracle's 64x64 buffer bit for bit."""
+import os
+import sys
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+f32 = np.float32
+
+
+def _rn(v: Fraction) -> np.float32:
+    """round a rational to f32, ties to even (exact: goes through the integer significand)"""
+    if v == 0:
+        return f32(0)
+    sign = -1 if v < 0 else 1
+    v = abs(v)
+    e = v.numerator.bit_length() - v.denominator.bit_length()
+    if Fraction(2) ** e > v:
+        e -= 1
+    scaled = v / Fraction(2) ** (e - 23)          # in [2^23, 2^24)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and n % 2 == 1):
+        n += 1
+    return f32(sign * float(n) * 2.0 ** (e - 23))
+
+
+@pytest.mark.parametrize("cnt", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_fma_division_equals_ieee_division(cnt):
+    for scale, smax in ((8, 8 * 8 * 255), (4, 8 * 4 * 255)):
+        d = f32(scale * cnt)
+        y = f32(f32(1) / d)
+        s = np.arange(0, smax + 1)
+        want = (s.astype(f32) / d).astype(f32)
+        q = (s.astype(np.float64) * np.float64(y)).astype(f32)           # exact product, one rounding
+        step = 1 if cnt in (3, 5, 6, 7) else 97
+        for k in range(0, smax + 1, step):
+            fq = Fraction(float(q[k]))
+            r = _rn(Fraction(k) - Fraction(float(d)) * fq)
+            got = _rn(Fraction(float(r)) * Fraction(float(y)) + fq)
+            assert got == want[k], (cnt, scale, k)
+
+
+def test_restructured_algorithm_is_bit_exact(orc):
+    import fused_model
+    from rupphash_b200.synth import synth_images
+    rng = np.random.default_rng(1)
+    for (h, w) in [(384, 512), (341, 512), (512, 512)]:
+        for luma in (orc.luma601(synth_images(1, h, w, seed=h)[0]).reshape(h, w),
+                     rng.integers(0, 256, size=(h, w), dtype=np.uint8)):
+            _, _, ref = orc.pdq_from_luma(luma)
+            got = fused_model.fused_buffer64(luma)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))

@@ -93,7 +93,9 @@ def test_hash_and_dihedral_from_coeffs(ctx, orc):
 
 @pytest.mark.parametrize("shape", [(768, 1024, 3), (512, 512, 3), (384, 512, 3), (384, 512, 4), (384, 512),
                                    (64, 64, 3), (5, 5, 3), (37, 5, 3), (300, 100, 3), (257, 511, 3), (100, 449, 3),
-                                   (720, 1024, 3), (1024, 640, 4), (480, 500)])
+                                   (720, 1024, 3), (1024, 640, 4), (480, 500), (1024, 1024, 3), (341, 512),
+                                   (700, 1024, 4), (900, 1024), (330, 512, 3), (449, 512, 3), (321, 512, 4),
+                                   (642, 1024, 3), (385, 512, 3)])
 def test_hash_batch_bit_exact(ctx, orc, shape):
     from rupphash_b200 import pdqhash
     h, w = shape[:2]
