@@ -15,6 +15,8 @@
 // edge rule (j > i, low-confidence => distance 0 only) and hooks the union-find.
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 
@@ -88,6 +90,14 @@ __device__ __host__ __forceinline__ int tile_owner(uint32_t qb, uint32_t cb, int
     return (int)((qb + cb) % (uint32_t)world);
 }
 
+// PF = 0: every pair gets the full 256-bit distance (dist256).
+// PF = 3 / 4: exact two-stage search.  The hot loop only measures the first PF words (96 / 128
+// bits) -- a lower bound of the distance -- with one carry-save step (2 POPC for PF = 3); a pair
+// whose partial distance already exceeds the threshold cannot be an edge.  For unrelated hashes
+// the partial distance is ~N(16 PF, 8 PF), so at threshold <= 32 (PF = 3) / <= 46 (PF = 4) fewer
+// than 1e-3 of the pairs survive; the survivors get the remaining words added and then take the
+// same exact slow path.  Results are identical to PF = 0 for any input.
+template <int PF>
 __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_kernel(const GroupArgs g) {
     const uint32_t cb = blockIdx.x, qb = blockIdx.y;
     if (tile_owner(qb, cb, g.world) != g.rank) return;
@@ -121,17 +131,37 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_kernel(const GroupAr
     uint32_t local_edges = 0;
 #pragma unroll 2
     for (int c = 0; c < cn; c++) {
-        const uint4 a = s_cand[2 * c], b = s_cand[2 * c + 1];
+        const uint4 a = s_cand[2 * c];
         uint32_t d[HT_RQ];
+        if (PF == 0) {
+            const uint4 b = s_cand[2 * c + 1];
 #pragma unroll
-        for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+            for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+        } else {
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) {
+                const uint32_t x0 = q[r][0] ^ a.x, x1 = q[r][1] ^ a.y, x2 = q[r][2] ^ a.z;
+                // p(s) + 2 p(c) as one IMAD: keeps the add off the (busier) LOP3/IADD pipe
+                asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d[r]) : "r"(__popc(maj3(x0, x1, x2))), "r"(__popc(xor3(x0, x1, x2))));
+                if (PF == 4) d[r] += __popc(q[r][3] ^ a.w);
+            }
+        }
         uint32_t m = d[0];
 #pragma unroll
         for (int r = 1; r < HT_RQ; r++) m = min(m, d[r]);
         if (m <= T) {
+            const uint4 b = s_cand[2 * c + 1];
 #pragma unroll
-            for (int r = 0; r < HT_RQ; r++)
-                if (d[r] <= T) local_edges += slow_hit(&s_g, d[r], qf[r], c0 + c);
+            for (int r = 0; r < HT_RQ; r++) {
+                if (d[r] > T) continue;
+                uint32_t full = d[r];
+                if (PF != 0) {
+                    if (PF == 3) full += __popc(q[r][3] ^ a.w);
+                    full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
+                            __popc(q[r][7] ^ b.w);
+                }
+                if (full <= T) local_edges += slow_hit(&s_g, full, qf[r], c0 + c);
+            }
         }
     }
     // one atomic per warp
@@ -371,9 +401,18 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr) {
     if (pr.n_qb > 65535u) return rh::fail(ctx, RH_EUNSUPPORTED, "more than 65535 x 1024 query rows");
     dim3 grid(pr.n_cb, pr.n_qb);
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
-    if (W == 8)
-        hamming_tiles_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
-    else
+    if (W == 8) {
+        // two-stage search when the threshold is low enough for the prefix filter to be selective
+        const char *force = getenv("RH_HAMMING_PREFILTER");   // "0" | "3" | "4": pin the variant (benchmarks)
+        int pf = pr.g.threshold <= 32 ? 3 : (pr.g.threshold <= 46 ? 4 : 0);
+        if (force) pf = atoi(force);
+        if (pf == 3)
+            hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        else if (pf == 4)
+            hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        else
+            hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
+    } else
         hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
     RH_LAUNCHED(ctx, "hamming_tiles_kernel");
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
