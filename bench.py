@@ -305,6 +305,12 @@ def main():
             labels = scanner.merge_forests(gathered, ctx)
             return labels, int(total.item()), kms
 
+        # the full-distance variant (8 words per pair, no prefix filter) for reference
+        os.environ["RH_HAMMING_PREFILTER"] = "0"
+        group_device()
+        _, _, full_ms = group_device()
+        full_ms = max_over_ranks(full_ms)
+        del os.environ["RH_HAMMING_PREFILTER"]
         group_device()
         barrier()
         reps = 3
@@ -332,16 +338,23 @@ def main():
                "value": pairs / wall_dev, "unit": "pairs/s", "tile_kernel_ms": tile_ms,
                "tile_kernel_pairs_per_s": pairs / (tile_ms * 1e-3) if tile_ms > 0 else None,
                "group_wall_ms_device_resident": wall_dev * 1e3, "group_wall_ms_e2e_pinned_host": wall_e2e * 1e3,
-               "edges": int(edges), "edges_e2e": int(edges2), "groups": None, "n_gpus": world,
+               "edges": int(edges), "edges_e2e": int(edges2), "n_gpus": world,
+               "kernel_variant": "two-stage: 96-bit prefix lower bound (2 POPC) + exact refine of survivors",
+               "full_distance_variant": {"tile_kernel_ms": full_ms,
+                                         "pairs_per_s": pairs / (full_ms * 1e-3) if full_ms > 0 else None,
+                                         "note": "every pair gets all 8 words: 16 LOP3 + 4 POPC (carry-save)"},
                "exchange": "none (1 GPU)" if world == 1 else "NCCL all-gather of n x u32 forests + all-reduce of edge counts"}
         if pk:
             peak_pairs = pk["popc_per_s"] / POPC_PER_PAIR
             per_gpu = pairs / world / (tile_ms * 1e-3)
             ham["roofline"] = {"bound": "int-pipe (POPC.32)", "achieved": per_gpu * POPC_PER_PAIR,
                                "peak": pk["popc_per_s"], "unit": "POPC/s", "frac": per_gpu / peak_pairs,
-                               "note": "algorithmic 8 POPC per pair over the measured POPC issue rate; the kernel "
-                                       "executes 4 POPC + 16 LOP3 per pair (carry-save), so frac may exceed 1",
-                               "lop3_frac": per_gpu * 16 / pk["lop3_per_s"]}
+                               "note": "algorithmic 8 POPC per pair over the measured POPC issue rate; the two-stage "
+                                       "kernel executes 2 POPC + 5 LOP3 per pair in its hot loop, so frac exceeds 1",
+                               "executed_popc_frac": per_gpu * 2 / pk["popc_per_s"],
+                               "executed_lop3_frac": per_gpu * 5 / pk["lop3_per_s"],
+                               "full_distance_variant_frac": (pairs / world / (full_ms * 1e-3)) / peak_pairs
+                               if full_ms > 0 else None}
         line["hamming"] = ham
 
     # ------------------------------------------------------------- CPU baseline (rank 0) ---

@@ -182,47 +182,69 @@ __device__ __forceinline__ void edge_p1(const uint8_t *sL, float *sE, int nL) {
 }
 
 struct EdgeState {
-    float sum, cnt;
+    float sum;
 };
 
 // Phase E2: the column chain of one inexact column (lane = column), continued across bands and
 // written in terms of the OUTPUT row o (box_one_d_float, pdqhash.rs:341-396, window WC, length H):
-//   grow   o in [0, HT]          sum += in[o+HB]; cnt += 1
+//   grow   o in [0, HT]          sum += in[o+HB]
 //   slide  o in [HT+1, H-HALF]   sum += in[o+HB]; sum -= in[o-HT-1]
-//   shrink o in [H-HALF+1, H-1]  sum -= in[o-HT-1]; cnt -= 1
-// Inputs P1 come from sE[slot(row)]; outputs P2 overwrite sE[slot(o)] (slot(o) < slot(o+HB), that
-// input has been consumed and parked in the 8-row ring by then).
+//   shrink o in [H-HALF+1, H-1]  sum -= in[o-HT-1]
+// Only the two dependent adds per row are sequential.  Rows go four at a time: the entering
+// values (sE[slot(row)]) and the leaving ones (an 8-row ring that survives across bands) are
+// loaded up front, so the loop runs at add latency; the running sums overwrite sE[slot(o)]
+// (slot(o) <= every input slot still unread) and are divided by the window size afterwards by
+// the whole CTA (edge_divide).
 template <int WC>
 __device__ __forceinline__ void edge_chain(EdgeState &st, float *sE, float *sRing, int lane, int H, int b0,
                                            int rows_out, int Lr0) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
-    for (int o = b0; o < b0 + rows_out; o++) {
-        if (o == 0) {  // pdqhash.rs:366-370: the leading half window, no output
-            for (int i = 0; i < HALF - 1; i++) {
-                const float x = sE[(i - Lr0) * 6 + lane];
-                st.sum = __fadd_rn(st.sum, x);
-                st.cnt += 1.0f;
-                sRing[(i & 7) * 6 + lane] = x;
+    static_assert(WC >= 4, "chunks of 4 rows need the leaving rows to predate the chunk");
+    if (b0 == 0) {  // pdqhash.rs:366-370: the leading half window, no output
+        for (int i = 0; i < HALF - 1; i++) {
+            const float x = sE[(i - Lr0) * 6 + lane];
+            st.sum = __fadd_rn(st.sum, x);
+            sRing[(i & 7) * 6 + lane] = x;
+        }
+    }
+    const int oend = b0 + rows_out;
+    for (int o0 = b0; o0 < oend; o0 += 4) {
+        float x[4], old[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = o0 + k, rin = o + HB, rout = o - HT - 1;
+            x[k] = (o < oend && rin < H) ? sE[(rin - Lr0) * 6 + lane] : 0.0f;
+            old[k] = (o < oend && rout >= 0) ? sRing[(rout & 7) * 6 + lane] : 0.0f;
+        }
+        float res[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = o0 + k;
+            if (o <= H - HALF) st.sum = __fadd_rn(st.sum, x[k]);   // grow and slide take a new row in
+            if (o > HT) st.sum = __fsub_rn(st.sum, old[k]);        // slide and shrink drop the oldest
+            res[k] = st.sum;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = o0 + k, rin = o + HB;
+            if (o < oend) {
+                if (rin < H) sRing[(rin & 7) * 6 + lane] = x[k];
+                sE[(o - Lr0) * 6 + lane] = res[k];
             }
         }
-        const int rin = o + HB, rout = o - HT - 1;
-        if (o <= HT) {
-            const float x = sE[(rin - Lr0) * 6 + lane];
-            st.sum = __fadd_rn(st.sum, x);
-            st.cnt += 1.0f;
-            sRing[(rin & 7) * 6 + lane] = x;
-        } else if (o <= H - HALF) {
-            const float x = sE[(rin - Lr0) * 6 + lane];
-            const float old = sRing[(rout & 7) * 6 + lane];  // read before the slot is reused (WC == 8)
-            st.sum = __fadd_rn(st.sum, x);
-            st.sum = __fsub_rn(st.sum, old);
-            sRing[(rin & 7) * 6 + lane] = x;
-        } else {
-            const float old = sRing[(rout & 7) * 6 + lane];
-            st.sum = __fsub_rn(st.sum, old);
-            st.cnt -= 1.0f;
-        }
-        sE[(o - Lr0) * 6 + lane] = __fdiv_rn(st.sum, st.cnt);
+    }
+}
+
+// sum / curr_win for the band's edge-column outputs (pdqhash.rs:375, :383, :392); curr_win is the
+// number of rows of the clipped column window
+template <int WC>
+__device__ __forceinline__ void edge_divide(float *sE, int H, int b0, int rows_out, int Lr0) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+    for (int idx = threadIdx.x; idx < rows_out * 6; idx += FTHREADS) {
+        const int o = b0 + idx / 6;
+        const int cnt = min(H - 1, o + HB) - max(0, o - HT) + 1;
+        float *p = sE + (o - Lr0) * 6 + (idx % 6);
+        *p = __fdiv_rn(*p, (float)cnt);
     }
 }
 
@@ -357,60 +379,81 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
 
 // ------------------------------------------------------------------------ tail ----
 
-// Pass 4 for decimated column j: the column chain over the pass-3 samples (window WC, length H),
-// keeping the 64 decimated rows (pdqhash.rs:435).
+// Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
+// columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
+// memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, all in flight), then
+// threads 0..63 (one per column) walk it at shared-memory latency.
+constexpr int P4_ROWS = 128;
+constexpr int P4_PITCH = P4_ROWS + 1;   // odd pitch: lane j reads bank (j + k) % 32
+static_assert(sizeof(TailSmem) + 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
+
 template <int WC>
-__device__ __forceinline__ void pass4_column(const float *col, int H, float *B, int j) {
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage) {
+    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
+    const int j = threadIdx.x;
     float sum = 0.0f, cnt = 0.0f;
     int i_next = 0, ini = H >> 7;   // ((2 i + 1) H) / 128 for i = 0
     float prev[8], cur[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-    for (int r0 = 0; r0 < H; r0 += 8) {
-        const float4 v0 = __ldcg(reinterpret_cast<const float4 *>(col + r0));
-        const float4 v1 = __ldcg(reinterpret_cast<const float4 *>(col + r0 + 4));
-        cur[0] = v0.x; cur[1] = v0.y; cur[2] = v0.z; cur[3] = v0.w;
-        cur[4] = v1.x; cur[5] = v1.y; cur[6] = v1.z; cur[7] = v1.w;
+    for (int c0 = 0; c0 < H; c0 += P4_ROWS) {
+        __syncthreads();   // the previous chunk has been consumed
+        for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
+            const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(p3t + (size_t)col * P3_PITCH + c0) + q);
+            float *d = stage + col * P4_PITCH + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncthreads();
+        if (j < 64) {
+            const float *colp = stage + j * P4_PITCH;
+            const int rows = min(P4_ROWS, H - c0);
+            for (int r0 = 0; r0 < rows; r0 += 8) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int ri = r0 + k;
-            if (ri >= H) break;
-            const float x = cur[k];
-            bool emit = true;
-            if (ri < HALF - 1) {
-                sum = __fadd_rn(sum, x);
-                cnt += 1.0f;
-                emit = false;
-            } else if (ri < WC) {
-                sum = __fadd_rn(sum, x);
-                cnt += 1.0f;
-            } else {
-                const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
-                sum = __fadd_rn(sum, x);
-                sum = __fsub_rn(sum, old);
+                for (int k = 0; k < 8; k++) cur[k] = colp[r0 + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int ri = c0 + r0 + k;
+                    if (ri >= H) break;
+                    const float x = cur[k];
+                    bool emit = true;
+                    if (ri < HALF - 1) {
+                        sum = __fadd_rn(sum, x);
+                        cnt += 1.0f;
+                        emit = false;
+                    } else if (ri < WC) {
+                        sum = __fadd_rn(sum, x);
+                        cnt += 1.0f;
+                    } else {
+                        const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
+                        sum = __fadd_rn(sum, x);
+                        sum = __fsub_rn(sum, old);
+                    }
+                    if (emit && ri - HB == ini) {
+                        B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
+                        i_next++;
+                        ini = ((2 * i_next + 1) * H) >> 7;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) prev[k] = cur[k];
             }
-            if (emit && ri - HB == ini) {
+        }
+    }
+    if (j < 64) {
+        // shrink phase: outputs H-HB .. H-1, leaving rows H-WC ..
+        const float *col = p3t + (size_t)j * P3_PITCH;
+        for (int k = 0; k < HALF - 1; k++) {
+            const float old = __ldcg(col + (H - WC + k));
+            sum = __fsub_rn(sum, old);
+            cnt -= 1.0f;
+            if (H - HB + k == ini && i_next < 64) {
                 B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
                 i_next++;
                 ini = ((2 * i_next + 1) * H) >> 7;
             }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) prev[k] = cur[k];
     }
-    // shrink phase: outputs H-HB .. H-1, leaving rows H-WC ..
-    for (int k = 0; k < HALF - 1; k++) {
-        const float old = __ldcg(col + (H - WC + k));
-        sum = __fsub_rn(sum, old);
-        cnt -= 1.0f;
-        if (H - HB + k == ini && i_next < 64) {
-            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
-            i_next++;
-            ini = ((2 * i_next + 1) * H) >> 7;
-        }
-    }
-    (void)HT;
 }
 
 template <int LAYOUT, bool DOWN2, int WC>
@@ -431,7 +474,6 @@ __global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs 
         const uint8_t *src = a.px + (size_t)img * a.img_pitch;
         EdgeState est;
         est.sum = 0.0f;
-        est.cnt = 0.0f;
         for (int b0 = 0; b0 < H; b0 += FBAND) {
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
@@ -442,11 +484,13 @@ __global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs 
             __syncthreads();
             if (warp == 7 && lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
             __syncthreads();
+            edge_divide<WC>(sE, H, b0, rows_out, Lr0);
+            __syncthreads();
             if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL);
             __syncthreads();
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
-        if (threadIdx.x < 64) pass4_column<WC>(p3t + (size_t)threadIdx.x * P3_PITCH, H, ts.B, threadIdx.x);
+        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + sizeof(TailSmem)));
         for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
         __syncthreads();
         const size_t oimg = (size_t)img + (size_t)a.out_offset;
