@@ -15,12 +15,14 @@
 //     decimated columns of pass 3, so only those are kept (64 floats per row).
 // The six inexact columns get the reference's real column chain (one lane each).
 //
-// Data flow per image (one CTA, 256 threads, ~75 KB shared memory, 3 CTAs per SM):
-//   for each band of 128 rows:
+// Data flow per image (one CTA, 8 + 1 warps, ~110 KB shared memory, 2 CTAs per SM, <= 112 registers
+// so the row chains keep their state in registers):
+//   for each band of 192 rows:
 //     F  all warps : global (128-bit loads, each pixel read once + 4 % halo) -> luma -> 2x2 rounded
 //                    average -> u8 luma band in shared memory (the only copy of the plane)
-//     E  edge cols : P1 of the six inexact columns, then their sequential column chains
-//     C  5-6 warps : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
+//     E  edge warp : (concurrently with F) P1 of the six inexact columns from its own loads of the
+//                    first / last 8-pixel chunk of each row, then their sequential column chains
+//     C  8 warps   : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
 //                    registers, vertical window sums come from warp shuffles, S2d -> float ->
 //                    FMA-corrected division -> pass-3 chain; 64 samples per row go to a per-CTA
 //                    L2-resident scratch (column-major, coalesced)
@@ -37,8 +39,9 @@ using namespace rh;
 constexpr int FW = 512;           // plane width served by this kernel
 constexpr int FLP = 528;          // luma row pitch in bytes: 512 + 16 zero bytes; 528 % 128 == 16
                                   // keeps the per-row LDS.128 of 8 consecutive lanes conflict-free
-constexpr int FBAND = 128;        // output rows per band
-constexpr int FTHREADS = 256;
+constexpr int FBAND = 192;        // output rows per band
+constexpr int FTHREADS = 288;     // 8 front-end / row-chain warps + 1 edge-column warp
+constexpr int FWORK = 256;        // threads that run the front end and the tail
 constexpr int FMAXL = FBAND + 7;  // luma rows per band including the vertical halo (window <= 8)
 constexpr int P3_PITCH = 512;     // floats per column of the pass-3 scratch
 constexpr size_t FSMEM = (size_t)FMAXL * FLP + (size_t)FMAXL * 6 * 4 + 8 * 6 * 4;
@@ -134,6 +137,7 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
     constexpr int NW = BYTES / 4;
+    if (threadIdx.x >= FWORK) return;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
     const uint8_t *colp = src + (size_t)col8 * BYTES;
     for (int s = rsub; s < nL; s += 8) {
@@ -167,17 +171,48 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
 
 // ---------------------------------------------------------------- edge columns ----
 
-// Phase E1: pass-1 values of the six columns whose clipped row window is 5, 6 or 7 wide
-// (box_one_d_float phases 2 and 4, pdqhash.rs:372-378, :389-395): rounded quotients.
-__device__ __forceinline__ void edge_p1(const uint8_t *sL, float *sE, int nL) {
-    for (int idx = threadIdx.x; idx < nL * 6; idx += FTHREADS) {
-        const int s = idx / 6, e = idx - 6 * s;
-        const int lo = e < 3 ? 0 : 502 + e;     // 505, 506, 507
-        const int hi = e < 3 ? 4 + e : 511;     // 4, 5, 6
-        const uint8_t *row = sL + (size_t)s * FLP;
-        int acc = 0;
-        for (int c = lo; c <= hi; c++) acc += row[c];
-        sE[idx] = __fdiv_rn((float)acc, (float)(hi - lo + 1));
+// Edge columns, step 1 (edge warp, lane = plane row): pass-1 values of the six columns whose
+// clipped row window is 5, 6 or 7 wide (box_one_d_float phases 2 and 4, pdqhash.rs:372-378,
+// :389-395) -- rounded quotients.  The edge warp reads the first and last 8-pixel chunk of each
+// row straight from global memory (the same lines the front-end warps fetch at about the same
+// time, so they come from L2) and therefore needs nothing from the other warps: the whole edge
+// pipeline runs concurrently with the front end.
+template <int LAYOUT, bool DOWN2>
+__device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
+                                        float *sE, int lane) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    constexpr int SPP = DOWN2 ? 2 : 1;
+    constexpr int BYTES = 8 * SPP * CH;
+    constexpr int NW = BYTES / 4;
+    for (int s = lane; s < nL; s += 32) {
+        const int lr = Lr0 + s;
+        if (lr < 0 || lr >= H) continue;
+        uint32_t l0[NW], l1[DOWN2 ? NW : 1], r0[NW], r1[DOWN2 ? NW : 1];
+        const uint8_t *pl = src + (size_t)(lr * SPP) * row_pitch;
+        const uint8_t *pr = pl + (size_t)63 * BYTES;
+        load_chunk<BYTES>(pl, l0);
+        load_chunk<BYTES>(pr, r0);
+        if (DOWN2) {
+            load_chunk<BYTES>(pl + row_pitch, l1);
+            load_chunk<BYTES>(pr + row_pitch, r1);
+        }
+        const uint2 vl = luma8<LAYOUT, DOWN2, NW>(l0, l1);   // plane columns 0..7
+        const uint2 vr = luma8<LAYOUT, DOWN2, NW>(r0, r1);   // plane columns 504..511
+        // column 0: [0,4], column 1: [0,5], column 2: [0,6]
+        const int s5 = (int)__dp4a(vl.x, 0x01010101u, 0u) + (int)(vl.y & 0xFFu);
+        const int s6 = s5 + (int)((vl.y >> 8) & 0xFFu);
+        const int s7 = s6 + (int)((vl.y >> 16) & 0xFFu);
+        // column 510: [507,511], column 509: [506,511], column 508: [505,511]
+        const int t5 = (int)__dp4a(vr.y, 0x01010101u, 0u) + (int)(vr.x >> 24);
+        const int t6 = t5 + (int)((vr.x >> 16) & 0xFFu);
+        const int t7 = t6 + (int)((vr.x >> 8) & 0xFFu);
+        float *o = sE + s * 6;
+        o[0] = __fdiv_rn((float)s5, 5.0f);
+        o[1] = __fdiv_rn((float)s6, 6.0f);
+        o[2] = __fdiv_rn((float)s7, 7.0f);
+        o[3] = __fdiv_rn((float)t7, 7.0f);
+        o[4] = __fdiv_rn((float)t6, 6.0f);
+        o[5] = __fdiv_rn((float)t5, 5.0f);
     }
 }
 
@@ -236,11 +271,11 @@ __device__ __forceinline__ void edge_chain(EdgeState &st, float *sE, float *sRin
 }
 
 // sum / curr_win for the band's edge-column outputs (pdqhash.rs:375, :383, :392); curr_win is the
-// number of rows of the clipped column window
+// number of rows of the clipped column window.  Run by the 32 lanes of the edge warp.
 template <int WC>
-__device__ __forceinline__ void edge_divide(float *sE, int H, int b0, int rows_out, int Lr0) {
+__device__ __forceinline__ void edge_divide(float *sE, int H, int b0, int rows_out, int Lr0, int lane) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
-    for (int idx = threadIdx.x; idx < rows_out * 6; idx += FTHREADS) {
+    for (int idx = lane; idx < rows_out * 6; idx += 32) {
         const int o = b0 + idx / 6;
         const int cnt = min(H - 1, o + HB) - max(0, o - HT) + 1;
         float *p = sE + (o - Lr0) * 6 + (idx % 6);
@@ -383,7 +418,7 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
 // columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
 // memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, all in flight), then
 // threads 0..63 (one per column) walk it at shared-memory latency.
-constexpr int P4_ROWS = 128;
+constexpr int P4_ROWS = 192;
 constexpr int P4_PITCH = P4_ROWS + 1;   // odd pitch: lane j reads bank (j + k) % 32
 static_assert(sizeof(TailSmem) + 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
 
@@ -457,7 +492,7 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
 }
 
 template <int LAYOUT, bool DOWN2, int WC>
-__global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sL = smem;
     float *sE = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);
@@ -465,7 +500,7 @@ __global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs 
     TailSmem &ts = *reinterpret_cast<TailSmem *>(smem);   // aliases the luma band, used after the last band
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, OPW = 33 - WC;
     constexpr int NWC = (FBAND + OPW - 1) / OPW;           // warps that run row chains
-    static_assert(NWC <= 7, "warp 7 is reserved for the edge columns");
+    static_assert(NWC <= 8, "warp 8 is reserved for the edge columns");
     const int H = a.H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *p3t = a.p3t + (size_t)blockIdx.x * 64 * P3_PITCH;
@@ -478,13 +513,15 @@ __global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs 
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
-            front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL);
-            __syncthreads();
-            edge_p1(sL, sE, nL);
-            __syncthreads();
-            if (warp == 7 && lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
-            __syncthreads();
-            edge_divide<WC>(sE, H, b0, rows_out, Lr0);
+            if (warp < 8) {
+                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL);
+            } else {   // the edge warp works alongside the front end
+                edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
+                __syncwarp();
+                if (lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
+                __syncwarp();
+                edge_divide<WC>(sE, H, b0, rows_out, Lr0, lane);
+            }
             __syncthreads();
             if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL);
             __syncthreads();
@@ -493,12 +530,14 @@ __global__ void __launch_bounds__(FTHREADS, 3) pdq_fused_kernel(const FusedArgs 
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + sizeof(TailSmem)));
         for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
         __syncthreads();
-        const size_t oimg = (size_t)img + (size_t)a.out_offset;
-        const float q = tail_quality(ts);
-        if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
-        tail_dct(ts);
-        if (a.out.coeffs) a.out.coeffs[oimg * 256 + threadIdx.x] = ts.C[threadIdx.x];
-        tail_hashes(ts, a.out, oimg);
+        if (threadIdx.x < FWORK) {   // the tail runs on 256 threads (named barrier 1)
+            const size_t oimg = (size_t)img + (size_t)a.out_offset;
+            const float q = tail_quality(ts);
+            if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
+            tail_dct(ts);
+            if (a.out.coeffs) a.out.coeffs[oimg * 256 + threadIdx.x] = ts.C[threadIdx.x];
+            tail_hashes(ts, a.out, oimg);
+        }
         __syncthreads();   // the next image's front end overwrites the aliased tail scratch
     }
 }
@@ -540,7 +579,7 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     if (!pdq_fused_supported(W, H)) return fail(ctx, RH_EUNSUPPORTED, "fused PDQ kernel: unsupported plane size");
     if ((reinterpret_cast<uintptr_t>(d_px) | row_pitch | img_pitch) & 15)
         return fail(ctx, RH_EINVAL, "fused PDQ kernel: pixels must be 16-byte aligned (pdq_fused_aligned)");
-    int grid = ctx->sm_count * 3;
+    int grid = ctx->sm_count * 2;
     if (grid > n) grid = (int)n;
     void *p;
     RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p));

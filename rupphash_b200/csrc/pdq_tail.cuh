@@ -11,6 +11,18 @@
 namespace rh {
 
 constexpr int TAIL_THREADS = 256;
+
+// The tail synchronises on named barrier 1 over exactly TAIL_THREADS threads, so that a kernel
+// with extra warps (pdq_fused_kernel's edge warp) can run it on its first 256 threads only.
+__device__ __forceinline__ void tail_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ int tail_count(bool pred) {
+    int n;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.popc.u32 %0, 1, 256, p;\n\t}"
+                 : "=r"(n)
+                 : "r"((unsigned)pred)
+                 : "memory");
+    return n;
+}
 constexpr int DCT_PITCH = 65;  // padded row pitch of the 16 x 64 DCT matrix in shared memory
 
 struct TailSmem {
@@ -57,7 +69,7 @@ __device__ __forceinline__ float block_rank127(float v) {
 #pragma unroll 1
     for (int bit = 31; bit >= 0; bit--) {
         const uint32_t b = 1u << bit;
-        const int c = __syncthreads_count(((key & mask) == prefix) && !(key & b));
+        const int c = tail_count(((key & mask) == prefix) && !(key & b));
         if (k >= c) {
             k -= c;
             prefix |= b;
@@ -93,7 +105,7 @@ __device__ __forceinline__ void tail_hashes(TailSmem &s, const TailOut &o, size_
         const float med = block_rank127(sv);
         s.bits[p][n] = sv > med;
     }
-    __syncthreads();
+    tail_sync();
     const int nt = 16 * c + r;  // transposed source: bit (r, c) of T(x) is bit (c, r) of x
     uint8_t *out = o.dihedral + img * 256;
     // order of pdqhash.rs:77-86
@@ -128,7 +140,7 @@ __device__ __forceinline__ float tail_quality(TailSmem &s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = acc;
-    __syncthreads();
+    tail_sync();
     float q = 0.0f;
     if (threadIdx.x == 0) {
         int tot = 0;
@@ -154,7 +166,7 @@ __device__ __forceinline__ void tail_dct(TailSmem &s) {
 #pragma unroll
         for (int u = 0; u < 4; u++) s.T[(i0 + u) * 64 + j] = acc[u];
     }
-    __syncthreads();
+    tail_sync();
     {   // C[i][j] = sum_k T[i][k] * D[j][k]
         const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
         float acc = 0.f;
@@ -162,7 +174,7 @@ __device__ __forceinline__ void tail_dct(TailSmem &s) {
         for (int k = 0; k < 64; k++) acc = __fadd_rn(acc, __fmul_rn(s.T[i * 64 + k], s.D[j * DCT_PITCH + k]));
         s.C[threadIdx.x] = acc;
     }
-    __syncthreads();
+    tail_sync();
 }
 
 }  // namespace rh
