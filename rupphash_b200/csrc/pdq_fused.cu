@@ -130,9 +130,15 @@ __device__ __forceinline__ uint2 luma8(const uint32_t *w0, const uint32_t *w1) {
 
 // Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
 // sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
+__device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+constexpr int PF_ROWS = 24;   // plane rows between the L2 prefetch front and the loads
+
 template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
-                                          uint8_t *sL) {
+__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, const uint8_t *__restrict__ next_src,
+                                          size_t row_pitch, int H, int Lr0, int nL, uint8_t *sL) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
@@ -146,6 +152,25 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
         const int lrA = Lr0 + sA, lrB = Lr0 + sB;
         const bool okA = lrA >= 0 && lrA < H;
         const bool okB = sB < nL && lrB >= 0 && lrB < H;
+        if (col8 == 0) {
+            // one thread per plane row pulls the source rows PF_ROWS ahead into L2 (a bulk prefetch
+            // per 3 KB row, no registers, no shared memory): the loads below then see L2 latency.
+            // The front runs past the band and into the next image, so band and image starts are warm.
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                int r = (t ? lrB : lrA) + PF_ROWS;
+                const uint8_t *base = src;
+                if (r >= H) {
+                    r -= H;
+                    base = next_src;
+                }
+                if (base != nullptr && r >= 0 && r < H) {
+                    const uint8_t *p = base + (size_t)(r * SPP) * row_pitch;
+                    l2_prefetch_row(p, BYTES * 64);
+                    if (DOWN2) l2_prefetch_row(p + row_pitch, BYTES * 64);
+                }
+            }
+        }
         if (okA) {
             const uint8_t *p = colp + (size_t)(lrA * SPP) * row_pitch;
             load_chunk<BYTES>(p, a0);
@@ -446,28 +471,42 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
             for (int r0 = 0; r0 < rows; r0 += 8) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) cur[k] = colp[r0 + k];
+                if (c0 + r0 >= 8 && c0 + r0 + 8 <= H) {
+                    // steady state (pdqhash.rs:380-387): every row slides, nothing to clip
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int ri = c0 + r0 + k;
-                    if (ri >= H) break;
-                    const float x = cur[k];
-                    bool emit = true;
-                    if (ri < HALF - 1) {
-                        sum = __fadd_rn(sum, x);
-                        cnt += 1.0f;
-                        emit = false;
-                    } else if (ri < WC) {
-                        sum = __fadd_rn(sum, x);
-                        cnt += 1.0f;
-                    } else {
+                    for (int k = 0; k < 8; k++) {
                         const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
-                        sum = __fadd_rn(sum, x);
-                        sum = __fsub_rn(sum, old);
+                        sum = __fsub_rn(__fadd_rn(sum, cur[k]), old);
+                        if (c0 + r0 + k - HB == ini) {
+                            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
+                            i_next++;
+                            ini = ((2 * i_next + 1) * H) >> 7;
+                        }
                     }
-                    if (emit && ri - HB == ini) {
-                        B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
-                        i_next++;
-                        ini = ((2 * i_next + 1) * H) >> 7;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int ri = c0 + r0 + k;
+                        if (ri >= H) break;
+                        const float x = cur[k];
+                        bool emit = true;
+                        if (ri < HALF - 1) {
+                            sum = __fadd_rn(sum, x);
+                            cnt += 1.0f;
+                            emit = false;
+                        } else if (ri < WC) {
+                            sum = __fadd_rn(sum, x);
+                            cnt += 1.0f;
+                        } else {
+                            const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
+                            sum = __fadd_rn(sum, x);
+                            sum = __fsub_rn(sum, old);
+                        }
+                        if (emit && ri - HB == ini) {
+                            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
+                            i_next++;
+                            ini = ((2 * i_next + 1) * H) >> 7;
+                        }
                     }
                 }
 #pragma unroll
@@ -507,6 +546,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
 
     for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
         const uint8_t *src = a.px + (size_t)img * a.img_pitch;
+        const uint8_t *next_src = img + gridDim.x < a.n ? src + (size_t)gridDim.x * a.img_pitch : nullptr;
         EdgeState est;
         est.sum = 0.0f;
         for (int b0 = 0; b0 < H; b0 += FBAND) {
@@ -514,7 +554,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
             if (warp < 8) {
-                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL);
+                front_end<LAYOUT, DOWN2>(src, next_src, a.row_pitch, H, Lr0, nL, sL);
             } else {   // the edge warp works alongside the front end
                 edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
                 __syncwarp();
