@@ -29,6 +29,8 @@
 //   T  pass 4 over the scratch (64 column chains), decimate, then pdq_tail.cuh.
 // HBM traffic is the pixels (read once) plus 36 B of results; the f32 planes of the reference
 // never exist.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pdq_tail.cuh"
 
@@ -57,6 +59,7 @@ struct FusedArgs {
     const float *dct;  // 16 x 64
     TailOut out;
     int64_t out_offset;
+    int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
 };
 
 // ------------------------------------------------------------------ front end ----
@@ -136,61 +139,81 @@ __device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes
 
 constexpr int PF_ROWS = 24;   // plane rows between the L2 prefetch front and the loads
 
+// Pull the source rows of plane rows [r0, r1) of the image at `base` into L2: one bulk prefetch per
+// 3 KB source row, no registers, no shared memory.
 template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, const uint8_t *__restrict__ next_src,
-                                          size_t row_pitch, int H, int Lr0, int nL, uint8_t *sL) {
+__device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row_pitch, int H, int r0, int r1,
+                                                 int first, int step) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    constexpr int SPP = DOWN2 ? 2 : 1;
+    constexpr uint32_t ROWB = 8 * SPP * CH * 64;
+    for (int r = max(r0, 0) + first; r < min(r1, H); r += step) {
+        const uint8_t *p = base + (size_t)(r * SPP) * row_pitch;
+        l2_prefetch_row(p, ROWB);
+        if (DOWN2) l2_prefetch_row(p + row_pitch, ROWB);
+    }
+}
+
+// Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep.  Each
+// thread ping-pongs between two register sets: the loads of its next row are issued before the
+// current row is converted, so 6 independent 128-bit loads per thread are always in flight under
+// the arithmetic.  An L2 prefetch front runs PF_ROWS rows ahead inside the band (not across a
+// row-chain phase: at ~3.5 TB/s a line survives only ~35 us in the 126 MB L2).
+template <int LAYOUT, bool DOWN2>
+__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
+                                          uint8_t *sL, int pf_mode) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
     constexpr int NW = BYTES / 4;
+    constexpr uint32_t ROWB = BYTES * 64;
     if (threadIdx.x >= FWORK) return;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
-    const uint8_t *colp = src + (size_t)col8 * BYTES;
-    for (int s = rsub; s < nL; s += 8) {
-        uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1];
-        const int sA = s, sB = s + 4;
-        const int lrA = Lr0 + sA, lrB = Lr0 + sB;
-        const bool okA = lrA >= 0 && lrA < H;
-        const bool okB = sB < nL && lrB >= 0 && lrB < H;
-        if (col8 == 0) {
-            // one thread per plane row pulls the source rows PF_ROWS ahead into L2 (a bulk prefetch
-            // per 3 KB row, no registers, no shared memory): the loads below then see L2 latency.
-            // The front runs past the band and into the next image, so band and image starts are warm.
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                int r = (t ? lrB : lrA) + PF_ROWS;
-                const uint8_t *base = src;
-                if (r >= H) {
-                    r -= H;
-                    base = next_src;
-                }
-                if (base != nullptr && r >= 0 && r < H) {
-                    const uint8_t *p = base + (size_t)(r * SPP) * row_pitch;
-                    l2_prefetch_row(p, BYTES * 64);
-                    if (DOWN2) l2_prefetch_row(p + row_pitch, BYTES * 64);
-                }
+    // slots whose plane row lies outside the image (top of the first band, bottom of the last) are
+    // stored as zeros, and so are the 16 pad bytes of every row: the chain phase needs no clipping
+    const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
+    for (int s = rsub; s < nL; s += 4) {
+        if (s < s_lo || s >= s_hi) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + col8 * 8) = make_uint2(0u, 0u);
+        if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
+    }
+    uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1];
+    const size_t rstep = (size_t)(4 * SPP) * row_pitch;            // 4 plane rows further down
+    int s = s_lo + rsub;
+    const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
+    uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
+    // the prefetch front of this thread (col8 == 0 only): its own rows, PF_ROWS ahead, inside the band
+    const uint8_t *pf = p + (size_t)(PF_ROWS * SPP) * row_pitch;
+    const bool pf_on = col8 == 0 && pf_mode >= 1;
+    if (s < s_hi) {
+        load_chunk<BYTES>(p, a0);
+        if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
+    }
+    while (s < s_hi) {
+        const bool haveB = s + 4 < s_hi;
+        if (haveB) {
+            load_chunk<BYTES>(p + rstep, b0);
+            if (DOWN2) load_chunk<BYTES>(p + rstep + row_pitch, b1);
+        }
+        if (pf_on) {
+            if (s + PF_ROWS < s_hi) {
+                l2_prefetch_row(pf, ROWB);
+                if (DOWN2) l2_prefetch_row(pf + row_pitch, ROWB);
+            }
+            if (s + 4 + PF_ROWS < s_hi) {
+                l2_prefetch_row(pf + rstep, ROWB);
+                if (DOWN2) l2_prefetch_row(pf + rstep + row_pitch, ROWB);
             }
         }
-        if (okA) {
-            const uint8_t *p = colp + (size_t)(lrA * SPP) * row_pitch;
-            load_chunk<BYTES>(p, a0);
-            if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
+        *reinterpret_cast<uint2 *>(d) = luma8<LAYOUT, DOWN2, NW>(a0, a1);
+        if (s + 8 < s_hi) {
+            load_chunk<BYTES>(p + 2 * rstep, a0);
+            if (DOWN2) load_chunk<BYTES>(p + 2 * rstep + row_pitch, a1);
         }
-        if (okB) {
-            const uint8_t *p = colp + (size_t)(lrB * SPP) * row_pitch;
-            load_chunk<BYTES>(p, b0);
-            if (DOWN2) load_chunk<BYTES>(p + row_pitch, b1);
-        }
-        // rows outside the image are stored as zeros: the chain phase then needs no clipping
-        uint2 vA = make_uint2(0u, 0u), vB = make_uint2(0u, 0u);
-        if (okA) vA = luma8<LAYOUT, DOWN2, NW>(a0, a1);
-        if (okB) vB = luma8<LAYOUT, DOWN2, NW>(b0, b1);
-        *reinterpret_cast<uint2 *>(sL + (size_t)sA * FLP + col8 * 8) = vA;
-        if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)sA * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
-        if (sB < nL) {
-            *reinterpret_cast<uint2 *>(sL + (size_t)sB * FLP + col8 * 8) = vB;
-            if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)sB * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
-        }
+        if (haveB) *reinterpret_cast<uint2 *>(d + 4 * FLP) = luma8<LAYOUT, DOWN2, NW>(b0, b1);
+        s += 8;
+        p += 2 * rstep;
+        pf += 2 * rstep;
+        d += 8 * FLP;
     }
 }
 
@@ -554,7 +577,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
             if (warp < 8) {
-                front_end<LAYOUT, DOWN2>(src, next_src, a.row_pitch, H, Lr0, nL, sL);
+                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode);
             } else {   // the edge warp works alongside the front end
                 edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
                 __syncwarp();
@@ -564,6 +587,14 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             }
             __syncthreads();
             if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL);
+            // warm L2 with the first PF_ROWS rows of whatever the front end loads next (the next band
+            // of this image, else the first band of the CTA's next image), a few us before it starts
+            if (lane == 0 && warp < 8 && a.pf_mode >= 2) {
+                if (b0 + FBAND < H)
+                    l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND - HT, b0 + FBAND - HT + PF_ROWS, warp, 8);
+                else if (next_src != nullptr)
+                    l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, PF_ROWS, warp, 8);
+            }
             __syncthreads();
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
@@ -633,6 +664,8 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     a.dct = d_dct;
     a.out = out;
     a.out_offset = out_offset;
+    const char *pfm = getenv("RH_PDQ_PREFETCH");
+    a.pf_mode = pfm ? atoi(pfm) : 2;
     const int wc = (H + 63) / 64;
     if (layout == RH_LAYOUT_RGB8)
         return down2 ? dispatch_wc<RH_LAYOUT_RGB8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGB8, false>(ctx, a, grid, wc);
