@@ -72,12 +72,15 @@ __device__ __forceinline__ void load_chunk(const uint8_t *p, uint32_t *w) {
             uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + i);
             w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
-    } else {
+    } else if (BYTES % 8 == 0) {
 #pragma unroll
         for (int i = 0; i < BYTES / 8; i++) {
             uint2 v = __ldg(reinterpret_cast<const uint2 *>(p) + i);
             w[2 * i] = v.x; w[2 * i + 1] = v.y;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < BYTES / 4; i++) w[i] = __ldg(reinterpret_cast<const uint32_t *>(p) + i);
     }
 }
 
@@ -131,14 +134,14 @@ __device__ __forceinline__ uint2 luma8(const uint32_t *w0, const uint32_t *w1) {
     return r;
 }
 
-// Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
-// sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
 __device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 constexpr int PF_ROWS = 24;   // plane rows between the L2 prefetch front and the loads
 
+// Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
+// sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
 // Pull the source rows of plane rows [r0, r1) of the image at `base` into L2: one bulk prefetch per
 // 3 KB source row, no registers, no shared memory.
 template <int LAYOUT, bool DOWN2>
