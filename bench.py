@@ -141,7 +141,7 @@ def synth_pool_device(torch, count, seed):
     return out
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be
     built here) on all host threads, same metric / config; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -171,13 +171,24 @@ def run_reference(args):
                          "sample": f"{per_step} images/step x {args.steps} steps"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     args = parse()
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's
+    # version banner, torchrun notices) is diverted to stderr until the result is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -400,7 +411,7 @@ def main():
                 "sample": f"full {n} hashes, oracle MIH probing + sequential union-find (scanner.rs:1673-1807)",
                 "labels_identical": bool(np.array_equal(lab, ref_labels)), "edges_identical": bool(ref_cnt == edges)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

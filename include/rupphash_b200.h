@@ -192,6 +192,23 @@ int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits
                    uint32_t *members, size_t members_cap, uint32_t *group_offsets,
                    size_t groups_cap, size_t *n_groups);
 
+/*
+ * max_dist of analyze_group_with_features (scanner.rs:2217-2241) for many groups at once: for
+ * group g, max over its members of (min over the pivot's variants of the Hamming distance).
+ *   pivot_variants    n_groups x 8 x 32 bytes: generate_dihedral_hashes of each group's pivot
+ *                     (or just its hash in slot 0 when the pivot has no cached coefficients,
+ *                     scanner.rs:2231-2237)
+ *   n_pivot_variants  n_groups bytes (1..8) or NULL (= 8)
+ *   member_hashes     n_members x 32 bytes, member_group n_members x u32 (group of each member;
+ *                     members without a hash are simply left out, scanner.rs:2221)
+ *   out_max_dist      n_groups x u32 (0 for a group without members)
+ * Choosing the pivot (the sort by duplicate status / stem, scanner.rs:2194-2214) is path and
+ * metadata logic and stays on the host.
+ */
+int rh_group_max_dist(rh_ctx *ctx, const uint8_t *pivot_variants, const uint8_t *n_pivot_variants,
+                      const uint8_t *member_hashes, const uint32_t *member_group, int64_t n_members,
+                      int64_t n_groups, uint32_t *out_max_dist);
+
 /* ------------------------------------------------------------- measurement ---- */
 
 /* Integer-pipe and copy peaks measured on this device, used as roofline denominators

@@ -28,7 +28,8 @@ EXPORTS = [
     "rh_phash_rotate_90", "rh_phash_rotate_180", "rh_phash_rotate_270", "rh_phash_flip_horizontal",
     "rh_phash_dihedral", "rh_phash_rotation_invariant", "rh_phash_batch",
     "rh_hamming_distances", "rh_hamming_distances_u64", "rh_hamming_group", "rh_hamming_group_shard",
-    "rh_uf_merge", "rh_hamming_edges", "rh_hamming_group_u64", "rh_find_groups", "rh_measure_peaks",
+    "rh_uf_merge", "rh_hamming_edges", "rh_hamming_group_u64", "rh_find_groups", "rh_group_max_dist",
+    "rh_measure_peaks",
 ]
 
 
@@ -99,6 +100,7 @@ def _declare(L):
                                        C.POINTER(C.c_uint64)]
     L.rh_find_groups.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_uint32, _vp, C.c_size_t, _vp, C.c_size_t,
                                  C.POINTER(C.c_size_t)]
+    L.rh_group_max_dist.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp]
     L.rh_measure_peaks.argtypes = [_vp, C.POINTER(C.c_double)]
 
 

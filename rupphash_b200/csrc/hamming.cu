@@ -300,6 +300,28 @@ __global__ void edges_to_sparse_kernel(uint2 *edges, unsigned long long cap, con
     edges[k] = make_uint2(cand_idx[e.x], cand_idx[e.y]);
 }
 
+// max over a group's members of (min over the pivot's variants of the Hamming distance):
+// analyze_group_with_features' max_dist (scanner.rs:2217-2241).  One thread per member.
+__global__ void group_max_dist_kernel(const uint8_t *pivots, const uint8_t *n_pivot_variants, const uint8_t *members,
+                                      const uint32_t *member_group, size_t m, uint32_t *out_max) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t g = member_group[i];
+    uint32_t h[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) h[w] = load_le32(members + i * 32 + w * 4);
+    const int nv = n_pivot_variants ? max(1, min((int)n_pivot_variants[g], 8)) : 8;
+    uint32_t best = 0xFFFFFFFFu;
+    for (int v = 0; v < nv; v++) {
+        const uint8_t *pv = pivots + ((size_t)g * 8 + v) * 32;
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) d += __popc(h[w] ^ load_le32(pv + w * 4));
+        best = min(best, d);
+    }
+    atomicMax(out_max + g, best);
+}
+
 struct Prepared {
     GroupArgs g;
     const uint32_t *valid, *dpos, *cand_idx;
@@ -637,6 +659,35 @@ int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits
         }
     }
     *n_groups = ng;
+    return RH_OK;
+}
+
+int rh_group_max_dist(rh_ctx *ctx, const uint8_t *pivot_variants, const uint8_t *n_pivot_variants,
+                      const uint8_t *member_hashes, const uint32_t *member_group, int64_t n_members, int64_t n_groups,
+                      uint32_t *out_max_dist) {
+    using namespace rh;
+    if (!ctx) return RH_EINVAL;
+    if (n_members < 0 || n_groups < 0 || (n_groups > 0 && (!pivot_variants || !out_max_dist)) ||
+        (n_members > 0 && (!member_hashes || !member_group)))
+        return fail(ctx, RH_EINVAL, "rh_group_max_dist: bad arguments");
+    if (n_groups == 0) return RH_OK;
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint8_t *d_piv, *d_nv, *d_mem;
+    const uint32_t *d_mg;
+    RH_TRY(stage_in(ctx, pivot_variants, (size_t)n_groups * 256, S_IN0, &d_piv));
+    RH_TRY(stage_in(ctx, n_pivot_variants, (size_t)n_groups, S_IN1, &d_nv));
+    RH_TRY(stage_in(ctx, member_hashes, (size_t)n_members * 32, S_IN2, &d_mem));
+    RH_TRY(stage_in(ctx, member_group, (size_t)n_members, S_IN3, &d_mg));
+    OutBuf<uint32_t> o;
+    RH_TRY(o.prepare(ctx, out_max_dist, (size_t)n_groups, S_OUT0));
+    RH_CUDA(ctx, cudaMemsetAsync(o.dev, 0, (size_t)n_groups * 4, st));
+    if (n_members > 0) {
+        group_max_dist_kernel<<<cdiv(n_members, 256), 256, 0, st>>>(d_piv, d_nv, d_mem, d_mg, (size_t)n_members, o.dev);
+        RH_LAUNCHED(ctx, "group_max_dist_kernel");
+    }
+    RH_TRY(o.finish(ctx));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
     return RH_OK;
 }
 

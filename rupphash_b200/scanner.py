@@ -169,6 +169,76 @@ def group_files_sharded(hashes, similarity, group=None, has_hash=None, variants=
     return labels, int(total.item())
 
 
+def merge_groups_by_stem(groups, paths):
+    """scanner.rs:1905-1983: groups that contain files with the same parent directory AND the same
+    file stem (e.g. IMG_1.jpg / IMG_1.cr2) are merged.  Host logic on paths; returns the groups in
+    canonical form (members ascending and de-duplicated, groups ordered by first member)."""
+    import os
+    if len(groups) < 2:
+        return [sorted(set(g)) for g in groups]
+    parent = list(range(len(groups)))
+
+    def find(i):
+        root = i
+        while parent[root] != root:
+            root = parent[root]
+        while parent[i] != root:
+            parent[i], i = root, parent[i]
+        return root
+
+    first_group_of = {}
+    for g_idx, group in enumerate(groups):
+        for f_idx in group:
+            p = paths[f_idx]
+            key = (os.path.dirname(p), os.path.splitext(os.path.basename(p))[0])
+            if not key[1]:
+                continue
+            other = first_group_of.setdefault(key, g_idx)
+            if other != g_idx:
+                ri, rj = find(other), find(g_idx)
+                if ri != rj:
+                    parent[ri] = rj
+    merged = {}
+    for g_idx, group in enumerate(groups):
+        merged.setdefault(find(g_idx), []).extend(group)
+    out = [sorted(set(g)) for g in merged.values()]
+    out.sort(key=lambda g: g[0])
+    return out
+
+
+def group_max_dist(groups, hashes, pivots, coefficients=None, has_hash=None, ctx=None):
+    """max_dist of every group (scanner.rs:2217-2241): max over the group's hashed members of the
+    minimum distance to the 8 dihedral variants of the group's pivot (or to the pivot's plain
+    hash when it has no cached coefficients).
+
+    groups: list of index lists; pivots: one file index per group (the caller's sort picks it:
+    the first member with features, else the first member with a hash); coefficients: (n, 256) f32
+    or None."""
+    ctx = ctx or default_context()
+    hashes = _u8(hashes).reshape(-1, 32)
+    ng = len(groups)
+    if ng == 0:
+        return np.zeros(0, np.uint32)
+    pivots = np.asarray(pivots, np.int64)
+    piv = np.zeros((ng, 8, 32), np.uint8)
+    piv[:, 0, :] = hashes[pivots]
+    nv = np.ones(ng, np.uint8)
+    if coefficients is not None:
+        piv[:] = np.asarray(pdqhash.dihedral_from_coeffs(np.ascontiguousarray(coefficients[pivots], np.float32), ctx))
+        nv[:] = 8
+    mem, grp = [], []
+    for g, members in enumerate(groups):
+        for i in members:
+            if has_hash is None or has_hash[i]:
+                mem.append(i)
+                grp.append(g)
+    mem_h = np.ascontiguousarray(hashes[np.asarray(mem, np.int64)]) if mem else np.zeros((0, 32), np.uint8)
+    grp = np.asarray(grp, np.uint32)
+    out = np.zeros(ng, np.uint32)
+    ctx.check(lib().rh_group_max_dist(ctx.handle, ptr(piv), ptr(nv), ptr(mem_h), ptr(grp), len(mem), ng, ptr(out)))
+    return out
+
+
 def hash_files_batched(images_iter, batch_size=256, want_coeffs=True, ctx=None, progress=None):
     """Scanner-style feeder (scanner.rs:1202-1521 restructured): decoded images of mixed sizes
     arrive one by one (the decode stays on the host, as in the reference); same-sized images

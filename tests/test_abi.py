@@ -107,3 +107,17 @@ def test_mih_index_bucket_matches_oracle(orc):
     for chunk in range(8):
         v = hamminghash.get_chunk(int(u[5]), chunk)
         assert mine.bucket(chunk, v).tolist() == ref.bucket(chunk, v).tolist()
+
+
+def test_merge_groups_by_stem():
+    """scanner.rs:1905-1983: groups sharing a (directory, stem) pair are merged, output canonical."""
+    from rupphash_b200 import scanner
+    paths = ["/a/IMG_1.jpg", "/a/IMG_2.jpg", "/a/IMG_1.cr2", "/a/x.png", "/b/IMG_1.jpg", "/b/y.jpg", "/a/.hidden",
+             "/a/IMG_2.tar.gz", "/a/IMG_2.tar.xz"]
+    groups = [[0, 3], [2, 5], [4, 6], [1, 7]]
+    # 0 and 2 share (/a, IMG_1) -> groups 0 and 1 merge; /b/IMG_1.jpg is another directory
+    assert scanner.merge_groups_by_stem(groups, paths) == [[0, 2, 3, 5], [1, 7], [4, 6]]
+    # stems are "IMG_2.tar" for both archives: merged through the shared stem
+    assert scanner.merge_groups_by_stem([[7, 0], [8, 4]], paths) == [[0, 4, 7, 8]]
+    assert scanner.merge_groups_by_stem([[3, 1, 1]], paths) == [[1, 3]]
+    assert scanner.merge_groups_by_stem([], paths) == []

@@ -240,3 +240,25 @@ def test_prefilter_variants_agree(ctx, orc, monkeypatch):
         labels, cnt = scanner.group_labels(hashes, 31, low_conf=low_conf, ctx=ctx)
         assert cnt == ref_cnt, pf
         assert np.array_equal(labels, ref_labels), pf
+
+
+def test_group_max_dist_matches_reference_rule(ctx, orc):
+    """scanner.rs:2217-2241: max over members of min over the pivot's 8 variants (or of the plain
+    pivot hash when it has no coefficients)."""
+    from rupphash_b200 import scanner
+    rng = np.random.default_rng(12)
+    n = 400
+    hashes, _ = planted_hashes(n, seed=3)
+    coeffs = (rng.standard_normal((n, 256)) * 30).astype(np.float32)
+    has_hash = (rng.random(n) > 0.1).astype(np.uint8)
+    groups = [sorted(rng.choice(n, size=int(rng.integers(2, 9)), replace=False).tolist()) for _ in range(60)]
+    pivots = [next(i for i in g if has_hash[i]) for g in groups]
+    got = scanner.group_max_dist(groups, hashes, pivots, coefficients=coeffs, has_hash=has_hash, ctx=ctx)
+    got_plain = scanner.group_max_dist(groups, hashes, pivots, has_hash=has_hash, ctx=ctx)
+    for g, members in enumerate(groups):
+        variants = orc.dihedral(coeffs[pivots[g]])
+        want = max(min(orc.hamming256(v, hashes[i]) for v in variants) for i in members if has_hash[i])
+        assert got[g] == want
+        want_plain = max(orc.hamming256(hashes[pivots[g]], hashes[i]) for i in members if has_hash[i])
+        assert got_plain[g] == want_plain
+    assert len(scanner.group_max_dist([], hashes, [], ctx=ctx)) == 0

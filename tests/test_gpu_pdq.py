@@ -222,3 +222,23 @@ def test_dihedral_robustness_like_reference(ctx):
         hsh = pdqhash.hash_batch(np.ascontiguousarray(t)[None], ctx=ctx)["hash"][0]
         d = hamminghash.hamming_distances(np.tile(hsh, (8, 1)), variants, ctx)
         assert d.min() <= 22
+
+
+def test_scanner_style_batching_feeder(ctx, orc):
+    """scanner.hash_files_batched: decoded images of mixed sizes arrive one by one, come back in
+    arrival order with the reference's per-file fields (hash, quality_100, coefficients) or None."""
+    from rupphash_b200 import scanner
+    shapes = [(384, 512, 3), (64, 64, 3), (384, 512, 3), (4, 100, 3), (768, 1024, 3), (64, 64, 3), (384, 512, 3)]
+    imgs = [synth_images(1, s[0], s[1], seed=11 * k + 1)[0] for k, s in enumerate(shapes)]
+    ticks = []
+    res = scanner.hash_files_batched(iter(imgs), batch_size=2, ctx=ctx, progress=lambda d, t: ticks.append((d, t)))
+    assert len(res) == len(imgs) and ticks
+    for k, img in enumerate(imgs):
+        ref = orc.pdq_features(img)
+        if ref is None:
+            assert res[k] is None
+            continue
+        coeffs, q, _ = ref
+        assert np.array_equal(res[k]["hash"], orc.to_hash(coeffs))
+        assert np.array_equal(res[k]["coeffs"], coeffs)
+        assert res[k]["quality"] == q and res[k]["quality_100"] == orc.quality_100(q)
