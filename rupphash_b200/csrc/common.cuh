@@ -25,7 +25,7 @@ struct rh_ctx {
     double last_ms = 0.0, last_units = 0.0;
     int sm_count = 148;
     // growable device scratch, one buffer per slot
-    static constexpr int kSlots = 24;
+    static constexpr int kSlots = 28;
     void *slot_ptr[kSlots] = {};
     size_t slot_bytes[kSlots] = {};
     // growable pinned host scratch
@@ -40,7 +40,8 @@ namespace rh {
 enum Slot {
     S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_IN4,   // staged inputs
     S_OUT0, S_OUT1, S_OUT2, S_OUT3, S_OUT4,  // staged outputs
-    S_W0, S_W1, S_W2, S_W3, S_W4, S_W5, S_W6, S_W7, S_W8, S_W9, S_W10, S_W11, S_W12, S_W13  // work
+    S_W0, S_W1, S_W2, S_W3, S_W4, S_W5, S_W6, S_W7, S_W8, S_W9, S_W10, S_W11, S_W12, S_W13,  // work
+    S_W14, S_W15, S_DCT  // S_DCT holds the PDQ DCT matrix for the life of the ctx
 };
 
 inline int fail(rh_ctx *ctx, int code, const char *what, cudaError_t ce = cudaSuccess) {

@@ -42,6 +42,8 @@ struct GroupArgs {
     unsigned long long *edges_n;
     uint32_t nc, nq, threshold;
     int rank, world;
+    const uint2 *tile_list;       // [n_tiles] (query block, candidate block) of every valid tile
+    uint32_t n_qb, n_tiles;
 };
 
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
@@ -84,10 +86,33 @@ __device__ __noinline__ uint32_t slow_hit(const GroupArgs *g, uint32_t d, uint32
     return 1;
 }
 
-// owner of a tile among `world` ranks: cyclic over anti-diagonals keeps every rank's share of
-// the upper triangle within one tile row of the others
-__device__ __host__ __forceinline__ int tile_owner(uint32_t qb, uint32_t cb, int world) {
-    return (int)((qb + cb) % (uint32_t)world);
+// first candidate block that can hold a pair with j > i for a query block whose smallest file id
+// is f0 (rows are ordered by file; scanner.rs:1712-1714), and the number of such blocks
+__device__ __forceinline__ uint32_t first_cand_block(uint32_t f0) { return (f0 + 1u) / (uint32_t)HT_TC; }
+
+// Only tiles that can contain work are launched: tile t (in the order query block major,
+// candidate block minor, valid tiles only) belongs to rank t mod world, so every rank gets the
+// same number of tiles to within one and no CTA is launched just to exit.
+__device__ __forceinline__ bool decode_tile(const GroupArgs &g, uint32_t &qb, uint32_t &cb) {
+    const uint32_t t = blockIdx.x * (uint32_t)g.world + (uint32_t)g.rank;
+    if (t >= g.n_tiles) return false;
+    const uint2 e = g.tile_list[t];
+    qb = e.x;
+    cb = e.y;
+    return true;
+}
+
+// (query block, candidate block) of every valid tile, in tile order: one thread per tile
+__global__ void tile_list_kernel(const uint32_t *tile_start, const uint32_t *qfile, uint32_t n_qb, uint32_t n_tiles,
+                                 uint2 *list) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t lo = 0, hi = n_qb;   // largest qb with tile_start[qb] <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tile_start[mid] <= t) lo = mid; else hi = mid;
+    }
+    list[t] = make_uint2(lo, first_cand_block(qfile[(size_t)lo * HT_TQ]) + (t - tile_start[lo]));
 }
 
 // PF = 0: every pair gets the full 256-bit distance (dist256).
@@ -98,14 +123,11 @@ __device__ __host__ __forceinline__ int tile_owner(uint32_t qb, uint32_t cb, int
 // than 1e-3 of the pairs survive; the survivors get the remaining words added and then take the
 // same exact slow path.  Results are identical to PF = 0 for any input.
 template <int PF>
-__global__ void __launch_bounds__(HT_THREADS) hamming_tiles_kernel(const GroupArgs g) {
-    const uint32_t cb = blockIdx.x, qb = blockIdx.y;
-    if (tile_owner(qb, cb, g.world) != g.rank) return;
+__global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const GroupArgs g) {
+    uint32_t cb, qb;
+    if (!decode_tile(g, qb, cb)) return;
     const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
     const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
-    // rows are ordered by file: the first row has the smallest file id of the block.  A tile
-    // whose last candidate is not above it holds no pair with j > i (scanner.rs:1712-1714).
-    if (!(c1 - 1 > g.qfile[q0])) return;
 
     __shared__ uint4 s_cand[HT_TC * 2];
     __shared__ GroupArgs s_g;
@@ -173,11 +195,10 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_kernel(const GroupAr
 // 64-bit hashes (hamminghash.rs:23-41): 2 words per hash, one thread per query row, the same
 // tile ownership.  Throughput is not a target here (no reference caller groups u64 hashes).
 __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_u64_kernel(const GroupArgs g) {
-    const uint32_t cb = blockIdx.x, qb = blockIdx.y;
-    if (tile_owner(qb, cb, g.world) != g.rank) return;
+    uint32_t cb, qb;
+    if (!decode_tile(g, qb, cb)) return;
     const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
     const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
-    if (!(c1 - 1 > g.qfile[q0])) return;
     __shared__ uint2 s_cand[HT_TC];
     __shared__ GroupArgs s_g;
     if (threadIdx.x == 0) s_g = g;
@@ -251,6 +272,19 @@ __global__ void scatter_kernel(const uint8_t *hashes, const uint8_t *variants, c
         qry[(size_t)(qo + v) * W + w] = load_le32(src + w * 4);
         if (w == 0) qfile[qo + v] = k;
     }
+}
+
+// number of candidate blocks that can hold a pair with j > i, per query block (entry n_qb = 0 so
+// that the exclusive scan ends with the total)
+__global__ void tile_counts_kernel(const uint32_t *qfile, uint32_t nc, uint32_t n_qb, uint32_t n_cb, uint32_t *counts) {
+    uint32_t qb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qb > n_qb) return;
+    uint32_t c = 0;
+    if (qb < n_qb) {
+        const uint32_t f0 = qfile[(size_t)qb * HT_TQ];
+        if (f0 != 0xFFFFFFFFu && f0 + 1u < nc) c = n_cb - min(n_cb, first_cand_block(f0));
+    }
+    counts[qb] = c;
 }
 
 __global__ void iota_kernel(uint32_t *p, uint32_t n) {
@@ -390,8 +424,33 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     }
     iota_kernel<<<cdiv(nc_pad, 256), 256, 0, st>>>(parent, (uint32_t)nc_pad);
     RH_LAUNCHED(ctx, "iota_kernel");
+    // the list of tiles that can contain a pair with j > i
+    const uint32_t n_qb = (uint32_t)(nq_pad / HT_TQ), n_cb = (uint32_t)(nc_pad / HT_TC);
+    uint32_t *tcount, *tstart;
+    RH_TRY(scratch(ctx, S_W12, (size_t)(n_qb + 1) * 4, &p)); tcount = (uint32_t *)p;
+    RH_TRY(scratch(ctx, S_W13, (size_t)(n_qb + 1) * 4, &p)); tstart = (uint32_t *)p;
+    tile_counts_kernel<<<cdiv(n_qb + 1, 256), 256, 0, st>>>(qfile, nc, n_qb, n_cb, tcount);
+    RH_LAUNCHED(ctx, "tile_counts_kernel");
+    size_t tmp2 = 0;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp2, tcount, tstart, (int)(n_qb + 1), st));
+    if (tmp2 > tmp_bytes) RH_TRY(scratch(ctx, S_W4, tmp2, &tmp));
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp2, tcount, tstart, (int)(n_qb + 1), st));
+    ctx->launches += 1;
+    uint32_t n_tiles = 0;
+    RH_CUDA(ctx, cudaMemcpyAsync(&n_tiles, tstart + n_qb, 4, cudaMemcpyDeviceToHost, st));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));
+
+    uint2 *tlist;
+    RH_TRY(scratch(ctx, S_W14, (size_t)(n_tiles ? n_tiles : 1) * sizeof(uint2), &p)); tlist = (uint2 *)p;
+    if (n_tiles) {
+        tile_list_kernel<<<cdiv(n_tiles, 256), 256, 0, st>>>(tstart, qfile, n_qb, n_tiles, tlist);
+        RH_LAUNCHED(ctx, "tile_list_kernel");
+    }
 
     GroupArgs &g = out->g;
+    g.tile_list = tlist;
+    g.n_qb = n_qb;
+    g.n_tiles = n_tiles;
     g.cand = cand;
     g.qry = qry;
     g.qfile = qfile;
@@ -409,8 +468,8 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     out->valid = valid;
     out->dpos = dpos;
     out->cand_idx = cand_idx;
-    out->n_cb = (uint32_t)(nc_pad / HT_TC);
-    out->n_qb = (uint32_t)(nq_pad / HT_TQ);
+    out->n_cb = n_cb;
+    out->n_qb = n_qb;
     return RH_OK;
 }
 
@@ -419,9 +478,8 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr) {
     cudaStream_t st = ctx->stream;
     ctx->last_ms = 0.0;
     ctx->last_units = 0.0;
-    if (pr.g.nc < 2 || pr.g.nq == 0) return RH_OK;
-    if (pr.n_qb > 65535u) return rh::fail(ctx, RH_EUNSUPPORTED, "more than 65535 x 1024 query rows");
-    dim3 grid(pr.n_cb, pr.n_qb);
+    if (pr.g.nc < 2 || pr.g.nq == 0 || pr.g.n_tiles == 0) return RH_OK;
+    const unsigned grid = rh::cdiv(pr.g.n_tiles, (size_t)pr.g.world);
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
     if (W == 8) {
         // two-stage search when the threshold is low enough for the prefix filter to be selective

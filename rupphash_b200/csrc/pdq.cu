@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) pdq_tail_kernel(const float *__r
 
 int ensure_dct(rh_ctx *ctx, const float **d_dct) {
     void *p;
-    RH_TRY(scratch(ctx, S_W13, 1024 * sizeof(float), &p));
+    RH_TRY(scratch(ctx, S_DCT, 1024 * sizeof(float), &p));
     if (!ctx->dct_ready) {
         float D[1024];
         host_dct_matrix(D);
