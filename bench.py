@@ -225,6 +225,12 @@ def main():
         return float(t.item())
 
     hbm_gbs, peak_src = peaks()
+    traffic_per_image = None   # dram read + write bytes per image of the dominant kernel, from the ncu capture
+    try:
+        traffic_per_image = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[
+            "pdq_fused_dram_bytes_per_image"]
+    except Exception:
+        pass
     B, K, W = args.batch, args.steps, args.warmup
 
     # ------------------------------------------------------------- PDQ, device resident ----
@@ -299,7 +305,11 @@ def main():
                 "matches_device_resident_hashes": same},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_gbs / hbm_gbs,
+                     "traffic": traffic_per_image * B if traffic_per_image else None,
+                     "traffic_source": "profiles/ncu_traffic.json (ncu dram read + write bytes per image x images "
+                                       "per launch)" if traffic_per_image else None,
+                     "peak_source": peak_src,
                      "kernel_ms_per_step": kernel_ms_per_step,
                      "algorithmic_bytes_per_image": ALGO_BYTES_PER_IMAGE},
     }

@@ -499,15 +499,24 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
                 for (int k = 0; k < 8; k++) cur[k] = colp[r0 + k];
                 if (c0 + r0 >= 8 && c0 + r0 + 8 <= H) {
                     // steady state (pdqhash.rs:380-387): every row slides, nothing to clip
+                    // The eight running sums are kept and the (one or two) decimated rows of
+                    // the batch are picked afterwards: no branch inside the dependent add chain.
+                    float sums[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
                         sum = __fsub_rn(__fadd_rn(sum, cur[k]), old);
-                        if (c0 + r0 + k - HB == ini) {
-                            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
-                            i_next++;
-                            ini = ((2 * i_next + 1) * H) >> 7;
-                        }
+                        sums[k] = sum;
+                    }
+                    const int base = c0 + r0 - HB;   // output row of sums[0]
+                    while (ini < base + 8 && i_next < 64) {
+                        const int k = ini - base;    // >= 0: earlier rows were emitted by earlier batches
+                        float v = sums[0];
+#pragma unroll
+                        for (int q = 1; q < 8; q++) v = (k == q) ? sums[q] : v;
+                        B[i_next * 64 + j] = __fdiv_rn(v, cnt);
+                        i_next++;
+                        ini = ((2 * i_next + 1) * H) >> 7;
                     }
                 } else {
 #pragma unroll
