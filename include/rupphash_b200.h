@@ -85,11 +85,11 @@ int rh_free_pinned(void *p);
  *   out_dihedral n x 8 x 32 bytes in the order of pdqhash.rs:77-86               [or NULL]
  *   out_valid   n bytes: 1 = Some, 0 = None (w < 5 or h < 5, pdqhash.rs:167-169)  [or NULL]
  *
- * Sizes: any w,h >= 5 with max(w,h) <= 512 (no pre-downsample, pdqhash.rs:181), and
- * sizes whose target dimensions (pdqhash.rs:224-235) are an exact 2x reduction in both
- * axes (1024x768 -> 512x384), for which the Box pre-downsample is two rounded halving
- * passes.  Other sizes return RH_EUNSUPPORTED (they need fast_image_resize's
- * fractional-weight convolution, which is not in the reference tree).
+ * Sizes: any w, h >= 5.  Images with a side above 512 px are pre-downsampled to the target
+ * dimensions of pdqhash.rs:224-235 like the reference does: an exact 2x reduction in both axes
+ * (1024x768 -> 512x384) is fused into the front end as two rounded halving passes; any other
+ * ratio runs fast_image_resize's fixed-point Box convolution as restated by the oracle (that
+ * crate is not in the reference tree: parity with it is unpinned).
  */
 int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h,
                       size_t row_pitch, size_t img_pitch, uint8_t *out_hash, float *out_quality,

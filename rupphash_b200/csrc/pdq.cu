@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "pdq_tail.cuh"
 
@@ -162,6 +164,108 @@ __global__ void __launch_bounds__(TAIL_THREADS) pdq_tail_kernel(const float *__r
     tail_hashes(s, o, oimg);
 }
 
+// ---- general Box pre-downsample (pdqhash.rs:203-220 -> fast_image_resize 6.1.0, U8 Convolution(Box)) ----
+// The crate is not in the reference tree; this follows the oracle's restatement of its
+// Pillow-derived algorithm (oracle_pdq.c orc_resize_box_u8): per axis, f64 box weights normalised
+// per output pixel, quantised to i16 at the largest precision that keeps the biggest coefficient
+// below 2^15; horizontal pass first into a u8 plane, then vertical, each pass computing
+// (sum(px * k) + (1 << (p-1))) >> p clipped to [0, 255].  PARITY UNPINNED w.r.t. the real crate.
+struct BoxCoeffs {
+    std::vector<int> xmin, cnt;
+    std::vector<int16_t> k;
+    int ksize = 0, precision = 0;
+};
+
+void box_precompute(int in_size, int out_size, BoxCoeffs *bc) {
+    const double scale = (double)in_size / (double)out_size;
+    const double fscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 0.5 * fscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    std::vector<double> pre((size_t)out_size * ksize, 0.0);
+    bc->xmin.assign(out_size, 0);
+    bc->cnt.assign(out_size, 0);
+    bc->k.assign((size_t)out_size * ksize, 0);
+    bc->ksize = ksize;
+    const double ss = 1.0 / fscale;
+    double maxk = 0.0;
+    for (int o = 0; o < out_size; o++) {
+        const double center = (o + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        const int cnt = xmax - xmin;
+        double ww = 0.0;
+        double *kk = pre.data() + (size_t)o * ksize;
+        for (int x = 0; x < cnt; x++) {
+            const double t = (x + xmin - center + 0.5) * ss;
+            const double wgt = (t > -0.5 && t <= 0.5) ? 1.0 : 0.0;
+            kk[x] = wgt;
+            ww += wgt;
+        }
+        for (int x = 0; x < cnt; x++) {
+            if (ww != 0.0) kk[x] /= ww;
+            if (kk[x] > maxk) maxk = kk[x];
+        }
+        bc->xmin[o] = xmin;
+        bc->cnt[o] = cnt;
+    }
+    int p;
+    for (p = 0; p < 32 - 8 - 2; p++) {
+        const int next = (int)(0.5 + maxk * (double)(1 << (p + 1)));
+        if (next >= (1 << 15)) break;
+    }
+    bc->precision = p;
+    for (size_t i = 0; i < pre.size(); i++) {
+        const double v = pre[i] * (double)(1 << p);
+        bc->k[i] = (int16_t)(v < 0 ? (int)(v - 0.5) : (int)(v + 0.5));
+    }
+}
+
+// one thread per output sample; `line_stride` / `tap_stride` walk the source along the filtered axis
+__global__ void box_resize_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n_img,
+                                  int out_w, int out_h, size_t src_img, int src_row, int tap_stride, bool vertical,
+                                  const int *__restrict__ xmin, const int *__restrict__ cnt,
+                                  const int16_t *__restrict__ k, int ksize, int precision) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t per = (size_t)out_w * out_h;
+    if (idx >= per * n_img) return;
+    const size_t img = idx / per;
+    const int y = (int)((idx % per) / out_w), x = (int)(idx % out_w);
+    const int o = vertical ? y : x;
+    const uint8_t *p = src + img * src_img + (vertical ? (size_t)xmin[o] * src_row + x : (size_t)y * src_row + xmin[o]);
+    const int16_t *kk = k + (size_t)o * ksize;
+    int acc = 1 << (precision - 1);
+    for (int t = 0; t < cnt[o]; t++) acc += (int)p[(size_t)t * tap_stride] * (int)kk[t];
+    acc >>= precision;
+    dst[idx] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+}
+
+struct DeviceBox {
+    const int *xmin, *cnt;
+    const int16_t *k;
+    int ksize, precision;
+};
+
+int upload_box(rh_ctx *ctx, const BoxCoeffs &bc, int slot, DeviceBox *out) {
+    const size_t n = bc.xmin.size();
+    const size_t bytes = n * 8 + bc.k.size() * 2;
+    void *p;
+    RH_TRY(scratch(ctx, slot, bytes, &p));
+    std::vector<uint8_t> host(bytes);
+    memcpy(host.data(), bc.xmin.data(), n * 4);
+    memcpy(host.data() + n * 4, bc.cnt.data(), n * 4);
+    memcpy(host.data() + n * 8, bc.k.data(), bc.k.size() * 2);
+    RH_CUDA(ctx, cudaMemcpyAsync(p, host.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `host` is a stack-lifetime object
+    out->xmin = (const int *)p;
+    out->cnt = out->xmin + n;
+    out->k = (const int16_t *)((const uint8_t *)p + n * 8);
+    out->ksize = bc.ksize;
+    out->precision = bc.precision;
+    return RH_OK;
+}
+
 int ensure_dct(rh_ctx *ctx, const float **d_dct) {
     void *p;
     RH_TRY(scratch(ctx, S_DCT, 1024 * sizeof(float), &p));
@@ -285,26 +389,38 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
     }
 
     int W = w, H = h;
-    bool down2 = false;
+    bool down2 = false, resize = false;
     if (w > 512 || h > 512) {  // pdqhash.rs:181-188
         target_dimensions(w, h, 512, &W, &H);
         if (W * 2 == w && H * 2 == h)
-            down2 = true;
+            down2 = true;      // two rounded halving passes, fused into the front end
         else
-            return fail(ctx, RH_EUNSUPPORTED,
-                        "rh_pdq_hash_batch: pre-downsample ratio other than exactly 2x is not implemented");
+            resize = true;     // general fixed-point Box convolution, run as its own kernels
+    }
+    DeviceBox bx{}, by{};
+    if (resize) {
+        BoxCoeffs cx, cy;
+        box_precompute(w, W, &cx);
+        box_precompute(h, H, &cy);
+        RH_TRY(upload_box(ctx, cx, S_W14, &bx));
+        RH_TRY(upload_box(ctx, cy, S_W15, &by));
     }
     const float *d_dct;
     RH_TRY(ensure_dct(ctx, &d_dct));
     TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
     const bool on_device = is_device_ptr(pixels);
     // host input is staged into 256-byte aligned buffers, so only the pitches matter there
-    const bool fused = pdq_fused_supported(W, H) != 0 &&
-                       pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) &&
-                       !getenv("RH_PDQ_FORCE_GENERIC");
+    const bool fused = pdq_fused_supported(W, H) != 0 && !getenv("RH_PDQ_FORCE_GENERIC") &&
+                       (resize ? (((size_t)W * H) & 15) == 0
+                               : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
     int64_t chunk = fused ? 2048 : 256;
+    if (resize) {   // full-resolution luma + the horizontally resized plane live in scratch
+        int64_t c3 = (int64_t)((size_t(1) << 30) / ((size_t)w * h + (size_t)W * h + (size_t)W * H));
+        if (c3 < 1) c3 = 1;
+        if (chunk > c3) chunk = c3;
+    }
     const size_t in_bytes_per = img_pitch;
     if (!on_device) {
         const size_t budget = size_t(512) << 20;
@@ -337,7 +453,32 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
             RH_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
             d_px = stage[b];
         }
-        if (fused)
+        if (resize) {
+            // luma at full resolution, Box-resize it (horizontal, then vertical), hash the planes
+            void *p;
+            RH_TRY(scratch(ctx, S_W5, (size_t)cn * w * h, &p));
+            uint8_t *Lfull = (uint8_t *)p;
+            RH_TRY(scratch(ctx, S_W6, (size_t)cn * W * h, &p));
+            uint8_t *Lh = (uint8_t *)p;
+            RH_TRY(scratch(ctx, S_W7, (size_t)cn * W * H, &p));
+            uint8_t *Lr = (uint8_t *)p;
+            if (layout == RH_LAYOUT_RGB8)
+                RH_TRY(launch_luma<RH_LAYOUT_RGB8>(ctx, false, d_px, row_pitch, img_pitch, (int)cn, w, h, Lfull));
+            else if (layout == RH_LAYOUT_RGBA8)
+                RH_TRY(launch_luma<RH_LAYOUT_RGBA8>(ctx, false, d_px, row_pitch, img_pitch, (int)cn, w, h, Lfull));
+            else
+                RH_TRY(launch_luma<RH_LAYOUT_LUMA8>(ctx, false, d_px, row_pitch, img_pitch, (int)cn, w, h, Lfull));
+            box_resize_kernel<<<cdiv((size_t)cn * W * h, 256), 256, 0, st>>>(Lfull, Lh, (size_t)cn, W, h, (size_t)w * h, w, 1,
+                                                                            false, bx.xmin, bx.cnt, bx.k, bx.ksize, bx.precision);
+            RH_LAUNCHED(ctx, "box_resize_kernel");
+            box_resize_kernel<<<cdiv((size_t)cn * W * H, 256), 256, 0, st>>>(Lh, Lr, (size_t)cn, W, H, (size_t)W * h, W, W,
+                                                                            true, by.xmin, by.cnt, by.k, by.ksize, by.precision);
+            RH_LAUNCHED(ctx, "box_resize_kernel");
+            if (fused)
+                RH_TRY(pdq_fused_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+            else
+                RH_TRY(generic_chunk(ctx, Lr, RH_LAYOUT_LUMA8, false, (int)cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+        } else if (fused)
             RH_TRY(pdq_fused_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
         else
             RH_TRY(generic_chunk(ctx, d_px, layout, down2, (int)cn, W, H, row_pitch, img_pitch, out, off, d_dct));

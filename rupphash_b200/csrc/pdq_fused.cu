@@ -60,6 +60,7 @@ struct FusedArgs {
     TailOut out;
     int64_t out_offset;
     int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
+    int pf_rows;       // plane rows between the prefetch front and the loads
 };
 
 // ------------------------------------------------------------------ front end ----
@@ -138,7 +139,7 @@ __device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-constexpr int PF_ROWS = 24;   // plane rows between the L2 prefetch front and the loads
+constexpr int PF_ROWS = 16;   // plane rows between the L2 prefetch front and the loads
 
 // Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
 // sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
@@ -164,7 +165,7 @@ __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row
 // row-chain phase: at ~3.5 TB/s a line survives only ~35 us in the 126 MB L2).
 template <int LAYOUT, bool DOWN2>
 __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
-                                          uint8_t *sL, int pf_mode) {
+                                          uint8_t *sL, int pf_mode, int pf_rows) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
@@ -185,7 +186,7 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
     uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
     // the prefetch front of this thread (col8 == 0 only): its own rows, PF_ROWS ahead, inside the band
-    const uint8_t *pf = p + (size_t)(PF_ROWS * SPP) * row_pitch;
+    const uint8_t *pf = p + (size_t)(pf_rows * SPP) * row_pitch;
     const bool pf_on = col8 == 0 && pf_mode >= 1;
     if (s < s_hi) {
         load_chunk<BYTES>(p, a0);
@@ -198,11 +199,11 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
             if (DOWN2) load_chunk<BYTES>(p + rstep + row_pitch, b1);
         }
         if (pf_on) {
-            if (s + PF_ROWS < s_hi) {
+            if (s + pf_rows < s_hi) {
                 l2_prefetch_row(pf, ROWB);
                 if (DOWN2) l2_prefetch_row(pf + row_pitch, ROWB);
             }
-            if (s + 4 + PF_ROWS < s_hi) {
+            if (s + 4 + pf_rows < s_hi) {
                 l2_prefetch_row(pf + rstep, ROWB);
                 if (DOWN2) l2_prefetch_row(pf + rstep + row_pitch, ROWB);
             }
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
             if (warp < 8) {
-                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode);
+                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
             } else {   // the edge warp works alongside the front end
                 edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
                 __syncwarp();
@@ -603,9 +604,9 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             // of this image, else the first band of the CTA's next image), a few us before it starts
             if (lane == 0 && warp < 8 && a.pf_mode >= 2) {
                 if (b0 + FBAND < H)
-                    l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND - HT, b0 + FBAND - HT + PF_ROWS, warp, 8);
+                    l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND - HT, b0 + FBAND - HT + a.pf_rows, warp, 8);
                 else if (next_src != nullptr)
-                    l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, PF_ROWS, warp, 8);
+                    l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, a.pf_rows, warp, 8);
             }
             __syncthreads();
         }
@@ -678,6 +679,8 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     a.out_offset = out_offset;
     const char *pfm = getenv("RH_PDQ_PREFETCH");
     a.pf_mode = pfm ? atoi(pfm) : 2;
+    const char *pfr = getenv("RH_PDQ_PREFETCH_ROWS");
+    a.pf_rows = pfr ? atoi(pfr) : PF_ROWS;
     const int wc = (H + 63) / 64;
     if (layout == RH_LAYOUT_RGB8)
         return down2 ? dispatch_wc<RH_LAYOUT_RGB8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGB8, false>(ctx, a, grid, wc);

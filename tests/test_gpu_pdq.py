@@ -140,10 +140,22 @@ def test_too_small_is_none(ctx):
     assert pdqhash.generate_pdq(np.zeros((4, 4), np.uint8), ctx) is None
 
 
-def test_unsupported_ratio_is_loud(ctx):
-    from rupphash_b200 import Unsupported, pdqhash
-    with pytest.raises(Unsupported):
-        pdqhash.hash_batch(np.zeros((1, 854, 1280, 3), np.uint8), ctx=ctx)
+@pytest.mark.parametrize("shape", [(854, 1280, 3), (720, 1080, 3), (768, 780, 3), (1280, 854, 3), (513, 513),
+                                   (600, 2000, 4), (1537, 640, 3), (5, 4000, 3)])
+def test_general_box_predownsample(ctx, orc, shape):
+    """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
+    convolution, restated by the oracle): fixed-point horizontal + vertical passes on the device."""
+    from rupphash_b200 import pdqhash
+    h, w = shape[:2]
+    ch = shape[2] if len(shape) == 3 else 1
+    imgs = synth_images(3, h, w, seed=3 * h + w, channels=ch)
+    if ch == 1:
+        imgs = imgs[..., 0]
+    layout = {3: 0, 4: 1, 1: 2}[ch]
+    want = orc.pdq_batch(imgs if ch > 1 else imgs[..., None], layout=layout, threads=4, want_coeffs=True,
+                         want_dihedral=True)
+    got = pdqhash.hash_batch(imgs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    check_exact(got, want)
 
 
 def test_single_image_api(ctx, orc):
@@ -201,6 +213,12 @@ def test_golden_fixtures(ctx, path):
     assert got["quality"][0] == g["quality"]
     assert np.array_equal(got["coeffs"][0], g["coeffs"])
     assert np.array_equal(got["dihedral"][0], g["dihedral"])
+    if "full_rgb" in g:   # the whole fixture image through the general Box pre-downsample
+        got = pdqhash.hash_batch(g["full_rgb"][None], want_coeffs=True, want_dihedral=True, ctx=ctx)
+        assert np.array_equal(got["hash"][0], g["hash"])
+        assert got["quality"][0] == g["quality"]
+        assert np.array_equal(got["coeffs"][0], g["coeffs"])
+        assert np.array_equal(got["dihedral"][0], g["dihedral"])
     if "crop_rgb" in g:
         got = pdqhash.hash_batch(g["crop_rgb"][None], want_coeffs=True, want_dihedral=True, ctx=ctx)
         assert np.array_equal(got["hash"][0], g["crop_hash"])

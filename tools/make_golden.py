@@ -12,6 +12,7 @@ Per fixture image the file holds
     hash/quality/coeffs/dihedral   oracle outputs for the full image
 and for the two images wide enough, an RGB crop whose pre-downsample is exactly 2x
     crop_rgb + crop_hash/crop_quality/crop_coeffs/crop_dihedral
+and prophecy1 also carries full_rgb, the whole decoded image (general Box pre-downsample path).
 """
 import os
 import sys
@@ -61,6 +62,10 @@ def main():
             cc, cq, _ = oracle.pdq_features(c)
             d.update(crop_rgb=c, crop_hash=oracle.to_hash(cc), crop_quality=np.float32(cq), crop_coeffs=cc,
                      crop_dihedral=oracle.dihedral(cc))
+        if name == "prophecy1":
+            # the whole decoded image (780 x 768 -> 512 x 504, a non-2x Box pre-downsample): the
+            # device must reproduce hash / quality / coefficients above from these pixels
+            d["full_rgb"] = rgb
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **d)
         print(name, rgb.shape, "->", luma.shape, bytes(d["hash"]).hex(), float(q), os.path.getsize(path))
