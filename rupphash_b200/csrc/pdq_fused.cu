@@ -55,6 +55,7 @@ struct FusedArgs {
     size_t row_pitch, img_pitch;
     int64_t n;
     int H;
+    const float *p2e;  // EDGEK: [n][H][6] pass-2 values of the six inexact columns (pdq_edge_kernel)
     float *p3t;        // [gridDim.x][64][P3_PITCH]
     const float *dct;  // 16 x 64
     TailOut out;
@@ -218,6 +219,70 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
         p += 2 * rstep;
         pf += 2 * rstep;
         d += 8 * FLP;
+    }
+}
+
+// Phase F with THREE register sets in rotation (the 8-warp / 128-register variant): the loads of a
+// thread's rows k+1 and k+2 are in flight while row k is converted, so an L2-latency load has two
+// conversions to land.
+template <int LAYOUT, bool DOWN2>
+__device__ __forceinline__ void front_end3(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
+                                           uint8_t *sL, int pf_mode, int pf_rows) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    constexpr int SPP = DOWN2 ? 2 : 1;
+    constexpr int BYTES = 8 * SPP * CH;
+    constexpr int NW = BYTES / 4;
+    constexpr uint32_t ROWB = BYTES * 64;
+    const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+    const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
+    for (int s = rsub; s < nL; s += 4) {
+        if (s < s_lo || s >= s_hi) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + col8 * 8) = make_uint2(0u, 0u);
+        if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
+    }
+    uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1], c0[NW], c1[DOWN2 ? NW : 1];
+    const size_t rstep = (size_t)(4 * SPP) * row_pitch;
+    int s = s_lo + rsub;
+    const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
+    uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
+    const uint8_t *pf = p + (size_t)(pf_rows * SPP) * row_pitch;
+    const bool pf_on = col8 == 0 && pf_mode >= 1;
+    if (s < s_hi) {
+        load_chunk<BYTES>(p, a0);
+        if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
+    }
+    if (s + 4 < s_hi) {
+        load_chunk<BYTES>(p + rstep, b0);
+        if (DOWN2) load_chunk<BYTES>(p + rstep + row_pitch, b1);
+    }
+    while (s < s_hi) {
+        if (s + 8 < s_hi) {
+            load_chunk<BYTES>(p + 2 * rstep, c0);
+            if (DOWN2) load_chunk<BYTES>(p + 2 * rstep + row_pitch, c1);
+        }
+        if (pf_on) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                if (s + 4 * q + pf_rows < s_hi) {
+                    l2_prefetch_row(pf + q * rstep, ROWB);
+                    if (DOWN2) l2_prefetch_row(pf + q * rstep + row_pitch, ROWB);
+                }
+            }
+        }
+        *reinterpret_cast<uint2 *>(d) = luma8<LAYOUT, DOWN2, NW>(a0, a1);
+        if (s + 12 < s_hi) {
+            load_chunk<BYTES>(p + 3 * rstep, a0);
+            if (DOWN2) load_chunk<BYTES>(p + 3 * rstep + row_pitch, a1);
+        }
+        if (s + 4 < s_hi) *reinterpret_cast<uint2 *>(d + 4 * FLP) = luma8<LAYOUT, DOWN2, NW>(b0, b1);
+        if (s + 16 < s_hi) {
+            load_chunk<BYTES>(p + 4 * rstep, b0);
+            if (DOWN2) load_chunk<BYTES>(p + 4 * rstep + row_pitch, b1);
+        }
+        if (s + 8 < s_hi) *reinterpret_cast<uint2 *>(d + 8 * FLP) = luma8<LAYOUT, DOWN2, NW>(c0, c1);
+        s += 12;
+        p += 3 * rstep;
+        pf += 3 * rstep;
+        d += 12 * FLP;
     }
 }
 
@@ -431,8 +496,8 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
 // Phase C for one band: lane = row.  Warp w owns luma slots [w OPW, w OPW + 31] of the band window
 // and produces output rows b0 + w OPW + lane for lane < OPW = 33 - WC.
 template <int WC>
-__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, float *p3t, int H, int b0,
-                                            int rows_out, int nL) {
+__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_rows, int p2e_first_row, int p2e_nrows,
+                                            float *p3t, int H, int b0, int rows_out, int nL) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro = warp * OPW + lane;   // output row within the band == luma slot of the window top
@@ -443,7 +508,8 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
     const float d8 = 8.0f * cnt, d4 = 4.0f * cnt;
     const float y8 = __frcp_rn(d8), y4 = __frcp_rn(d4);
     const uint8_t *rowp = sL + (size_t)min(ro, nL - 1) * FLP;
-    const float *p2e = sE + min(ro + HT, nL - 1) * 6;
+    // edge-column values of plane row r: p2e_rows holds rows [p2e_first_row, p2e_first_row + p2e_nrows)
+    const float *p2e = p2e_rows + (size_t)min(r - p2e_first_row, p2e_nrows - 1) * 6;
     float *p3col = p3t + r;
     ChainState st;
     st.aprev = 0u;
@@ -485,7 +551,7 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     for (int k = 0; k < 8; k++) prev[k] = 0.0f;
     for (int c0 = 0; c0 < H; c0 += P4_ROWS) {
         __syncthreads();   // the previous chunk has been consumed
-        for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
+        for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += blockDim.x) {
             const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(p3t + (size_t)col * P3_PITCH + c0) + q);
             float *d = stage + col * P4_PITCH + 4 * q;
@@ -566,8 +632,8 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     }
 }
 
-template <int LAYOUT, bool DOWN2, int WC>
-__global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
+template <int LAYOUT, bool DOWN2, int WC, bool EDGEK>
+__global__ void __launch_bounds__(EDGEK ? FWORK : FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sL = smem;
     float *sE = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);
@@ -589,7 +655,11 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
-            if (warp < 8) {
+            if (EDGEK) {
+                // 8 warps, up to 128 registers: three register sets of loads in flight; the edge
+                // columns were computed by pdq_edge_kernel
+                front_end3<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
+            } else if (warp < 8) {
                 front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
             } else {   // the edge warp works alongside the front end
                 edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
@@ -599,7 +669,12 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
                 edge_divide<WC>(sE, H, b0, rows_out, Lr0, lane);
             }
             __syncthreads();
-            if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL);
+            if (warp < NWC) {
+                if (EDGEK)
+                    chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, 0, H, p3t, H, b0, rows_out, nL);
+                else
+                    chain_phase<WC>(sL, sE, Lr0, nL, p3t, H, b0, rows_out, nL);
+            }
             // warm L2 with the first PF_ROWS rows of whatever the front end loads next (the next band
             // of this image, else the first band of the CTA's next image), a few us before it starts
             if (lane == 0 && warp < 8 && a.pf_mode >= 2) {
@@ -612,7 +687,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + sizeof(TailSmem)));
-        for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
+        for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
         __syncthreads();
         if (threadIdx.x < FWORK) {   // the tail runs on 256 threads (named barrier 1)
             const size_t oimg = (size_t)img + (size_t)a.out_offset;
@@ -626,12 +701,57 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
     }
 }
 
+// The six inexact columns for a whole chunk of images, one warp per image (the 8-warp variant of
+// the main kernel has no edge warp): the same edge_p1 -> edge_chain -> edge_divide pipeline over
+// blocks of EDGE_ROWS rows, results to p2e[img][row][6].  It reads the first and last 48-byte chunk
+// of every source row (~4 % of the pixels) and finishes in tens of microseconds.
+constexpr int EDGE_ROWS = 96;
+
+template <int LAYOUT, bool DOWN2, int WC>
+__global__ void __launch_bounds__(256) pdq_edge_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch,
+                                                       int64_t n, int H, float *__restrict__ p2e) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF;
+    __shared__ float s_e[8][(EDGE_ROWS + 7) * 6];
+    __shared__ float s_ring[8][8 * 6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t img = (int64_t)blockIdx.x * 8 + warp;
+    if (img >= n) return;   // warps are independent: no block-wide barrier below
+    const uint8_t *src = px + (size_t)img * img_pitch;
+    float *sE = s_e[warp], *sRing = s_ring[warp];
+    EdgeState est;
+    est.sum = 0.0f;
+    for (int b0 = 0; b0 < H; b0 += EDGE_ROWS) {
+        const int rows_out = min(EDGE_ROWS, H - b0);
+        const int Lr0 = b0 - HT;
+        const int nL = rows_out + WC - 1;
+        edge_p1<LAYOUT, DOWN2>(src, row_pitch, H, Lr0, nL, sE, lane);
+        __syncwarp();
+        if (lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
+        __syncwarp();
+        edge_divide<WC>(sE, H, b0, rows_out, Lr0, lane);
+        __syncwarp();
+        float *out = p2e + ((size_t)img * H + b0) * 6;
+        for (int idx = lane; idx < rows_out * 6; idx += 32) out[idx] = sE[HT * 6 + idx];
+        __syncwarp();
+    }
+}
+
 template <int LAYOUT, bool DOWN2, int WC>
 int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
-    auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC>;
-    RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
-    kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
-    RH_LAUNCHED(ctx, "pdq_fused_kernel");
+    if (a.p2e != nullptr) {
+        pdq_edge_kernel<LAYOUT, DOWN2, WC><<<cdiv((size_t)a.n, 8), 256, 0, ctx->stream>>>(
+            a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
+        RH_LAUNCHED(ctx, "pdq_edge_kernel");
+        auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC, true>;
+        RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
+        kern<<<grid, FWORK, FSMEM, ctx->stream>>>(a);
+        RH_LAUNCHED(ctx, "pdq_fused_kernel");
+    } else {
+        auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC, false>;
+        RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
+        kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
+        RH_LAUNCHED(ctx, "pdq_fused_kernel");
+    }
     return RH_OK;
 }
 
@@ -668,6 +788,13 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     void *p;
     RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p));
     FusedArgs a;
+    a.p2e = nullptr;
+    const char *ek = getenv("RH_PDQ_EDGE_KERNEL");   // default: 8-warp main kernel + separate edge-column kernel
+    if (!(ek && ek[0] == '0')) {
+        void *pe;
+        RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &pe));
+        a.p2e = (const float *)pe;
+    }
     a.px = d_px;
     a.row_pitch = row_pitch;
     a.img_pitch = img_pitch;
