@@ -58,3 +58,24 @@ def test_restructured_algorithm_is_bit_exact(orc):
             _, _, ref = orc.pdq_from_luma(luma)
             got = fused_model.fused_buffer64(luma)
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_fp32_fma_divides_luma_by_1000_exactly():
+    """pdq_fused.cu luma_px: floor(v / 1000) + 1 from one FP32 FMA on the DP2A accumulator, for every
+    v = 299 r + 587 g + 114 b + 500 the kernel can see.  The FMA is evaluated here in exact integer
+    arithmetic (mantissa of the f32 constant x F, one round-to-nearest-even at the end)."""
+    c = np.float32(0.0005)
+    mant, exp = np.frexp(c)                       # c = mant * 2**exp, mant in [0.5, 1)
+    m24 = int(np.ldexp(mant, 24))                 # 24-bit integer mantissa
+    shift = 24 - int(exp)                         # c = m24 / 2**shift
+    assert np.float32(m24 / 2.0 ** shift) == c
+    v = np.arange(0, 256001, dtype=np.int64)
+    F = 8388608 + 1392 + 1001 + 2 * v             # the float the DP2A pair leaves, as an integer
+    assert F.max() < 2 ** 24
+    exact = F * m24 + (8384413 << shift)          # (F * c + M2) * 2**shift, exact
+    assert (exact >> shift).min() >= 2 ** 23 and (exact >> shift).max() < 2 ** 24   # ulp(result) == 1
+    half = 1 << (shift - 1)
+    frac = exact & ((1 << shift) - 1)
+    assert (frac != half).all()                   # no ties
+    rn = (exact + half) >> shift
+    assert np.array_equal(rn - 8388608, v // 1000 + 1)
