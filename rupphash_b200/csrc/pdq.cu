@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) pdq_tail_kernel(const float *__r
     __syncthreads();
     const float q = tail_quality(s);
     if (threadIdx.x == 0 && o.quality) o.quality[oimg] = q;
-    tail_dct(s);
+    tail_dct(s, s.D);
     if (o.coeffs) o.coeffs[oimg * 256 + threadIdx.x] = s.C[threadIdx.x];
     tail_hashes(s, o, oimg);
 }

@@ -15,17 +15,19 @@
 //     decimated columns of pass 3, so only those are kept (64 floats per row).
 // The six inexact columns get the reference's real column chain (one lane each).
 //
-// Data flow per image (one CTA, 8 + 1 warps, ~110 KB shared memory, 2 CTAs per SM, <= 112 registers
-// so the row chains keep their state in registers):
+// Data flow.  pdq_edge_kernel first runs the six inexact columns of every image of the chunk
+// (one warp per image; it reads the first / last 48 source bytes of each row, ~4 % of the pixels)
+// and leaves their pass-2 values in a [n][H][6] scratch.  Then, per image (one CTA, 8 warps,
+// ~108 KB shared memory, 2 CTAs per SM, <= 128 registers so the row chains keep their state in
+// registers):
 //   for each band of 192 rows:
-//     F  all warps : global (128-bit loads, each pixel read once + 4 % halo) -> luma -> 2x2 rounded
-//                    average -> u8 luma band in shared memory (the only copy of the plane)
-//     E  edge warp : (concurrently with F) P1 of the six inexact columns from its own loads of the
-//                    first / last 8-pixel chunk of each row, then their sequential column chains
-//     C  8 warps   : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
-//                    registers, vertical window sums come from warp shuffles, S2d -> float ->
-//                    FMA-corrected division -> pass-3 chain; 64 samples per row go to a per-CTA
-//                    L2-resident scratch (column-major, coalesced)
+//     F  8 warps : global (128-bit loads, three register sets in rotation, each pixel read once
+//                  + 4 % halo) -> luma -> 2x2 rounded average -> u8 luma band in shared memory
+//                  (the only copy of the plane)
+//     C  8 warps : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
+//                  registers, vertical window sums come from warp shuffles, S2d -> float ->
+//                  two-term-reciprocal division -> pass-3 chain; 64 samples per row go to a
+//                  per-CTA L2-resident scratch (column-major, coalesced)
 //   T  pass 4 over the scratch (64 column chains), decimate, then pdq_tail.cuh.
 // HBM traffic is the pixels (read once) plus 36 B of results; the f32 planes of the reference
 // never exist.
@@ -42,11 +44,10 @@ constexpr int FW = 512;           // plane width served by this kernel
 constexpr int FLP = 528;          // luma row pitch in bytes: 512 + 16 zero bytes; 528 % 128 == 16
                                   // keeps the per-row LDS.128 of 8 consecutive lanes conflict-free
 constexpr int FBAND = 192;        // output rows per band
-constexpr int FTHREADS = 288;     // 8 front-end / row-chain warps + 1 edge-column warp
-constexpr int FWORK = 256;        // threads that run the front end and the tail
+constexpr int FTHREADS = 256;     // 8 warps: front end, row chains, tail
 constexpr int FMAXL = FBAND + 7;  // luma rows per band including the vertical halo (window <= 8)
 constexpr int P3_PITCH = 512;     // floats per column of the pass-3 scratch
-constexpr size_t FSMEM = (size_t)FMAXL * FLP + (size_t)FMAXL * 6 * 4 + 8 * 6 * 4;
+constexpr size_t FSMEM = (size_t)FMAXL * FLP + 16 * DCT_PITCH * 4;   // luma band (aliased by the tail) + DCT matrix
 
 static_assert(sizeof(TailSmem) <= (size_t)FMAXL * FLP, "tail scratch must fit in the luma band");
 
@@ -55,14 +56,18 @@ struct FusedArgs {
     size_t row_pitch, img_pitch;
     int64_t n;
     int H;
-    const float *p2e;  // EDGEK: [n][H][6] pass-2 values of the six inexact columns (pdq_edge_kernel)
+    const float *p2e;  // [n][H][6] pass-2 values of the six inexact columns (pdq_edge_kernel)
     float *p3t;        // [gridDim.x][64][P3_PITCH]
     const float *dct;  // 16 x 64
     TailOut out;
     int64_t out_offset;
     int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
     int pf_rows;       // plane rows between the prefetch front and the loads
+    uint32_t magic;    // 0x4B000000 (bits of 2^23), passed in so that it lives in a register: div_exact
+    unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
 };
+
+enum { PH_FRONT = 0, PH_CHAIN, PH_P4_STAGE, PH_P4_CHAIN, PH_TAIL, NPHASE };
 
 // ------------------------------------------------------------------ front end ----
 
@@ -153,8 +158,6 @@ __device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes
 
 constexpr int PF_ROWS = 16;   // plane rows between the L2 prefetch front and the loads
 
-// Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep, two
-// sweeps in flight so that each thread has up to 12 independent 128-bit loads outstanding.
 // Pull the source rows of plane rows [r0, r1) of the image at `base` into L2: one bulk prefetch per
 // 3 KB source row, no registers, no shared memory.
 template <int LAYOUT, bool DOWN2>
@@ -171,10 +174,13 @@ __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row
 }
 
 // Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep.  Each
-// thread ping-pongs between two register sets: the loads of its next row are issued before the
-// current row is converted, so 6 independent 128-bit loads per thread are always in flight under
-// the arithmetic.  An L2 prefetch front runs PF_ROWS rows ahead inside the band (not across a
-// row-chain phase: at ~3.5 TB/s a line survives only ~35 us in the 126 MB L2).
+// thread rotates through SETS register sets (3 for RGB / luma: 72 registers of pixels; 2 for RGBA):
+// the loads of its rows k+1 .. k+SETS-1 are in flight while row k is converted (12 independent
+// 128-bit loads per thread), so an L2-latency load has two conversions to land.  An L2 prefetch
+// front runs PF_ROWS rows ahead inside the band (not across a row-chain phase: at ~4 TB/s a line
+// survives only ~30 us in the 126 MB L2).
+// Slots whose plane row lies outside the image (top of the first band, bottom of the last) are
+// stored as zeros, and so are the 16 pad bytes of every row: the chain phase needs no clipping.
 template <int LAYOUT, bool DOWN2>
 __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
                                           uint8_t *sL, int pf_mode, int pf_rows) {
@@ -182,118 +188,53 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
     constexpr int NW = BYTES / 4;
+    constexpr int SETS = NW * SPP * 3 <= 72 ? 3 : 2;
     constexpr uint32_t ROWB = BYTES * 64;
-    if (threadIdx.x >= FWORK) return;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
-    // slots whose plane row lies outside the image (top of the first band, bottom of the last) are
-    // stored as zeros, and so are the 16 pad bytes of every row: the chain phase needs no clipping
     const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
     for (int s = rsub; s < nL; s += 4) {
         if (s < s_lo || s >= s_hi) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + col8 * 8) = make_uint2(0u, 0u);
         if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
     }
-    uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1];
+    uint32_t w0[SETS][NW], w1[SETS][DOWN2 ? NW : 1];
     const size_t rstep = (size_t)(4 * SPP) * row_pitch;            // 4 plane rows further down
     int s = s_lo + rsub;
     const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
     uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
-    // the prefetch front of this thread (col8 == 0 only): its own rows, PF_ROWS ahead, inside the band
+    // the prefetch front of this thread (col8 == 0 only): its own rows, pf_rows ahead, inside the band
     const uint8_t *pf = p + (size_t)(pf_rows * SPP) * row_pitch;
     const bool pf_on = col8 == 0 && pf_mode >= 1;
-    if (s < s_hi) {
-        load_chunk<BYTES>(p, a0);
-        if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
-    }
-    while (s < s_hi) {
-        const bool haveB = s + 4 < s_hi;
-        if (haveB) {
-            load_chunk<BYTES>(p + rstep, b0);
-            if (DOWN2) load_chunk<BYTES>(p + rstep + row_pitch, b1);
-        }
-        if (pf_on) {
-            if (s + pf_rows < s_hi) {
-                l2_prefetch_row(pf, ROWB);
-                if (DOWN2) l2_prefetch_row(pf + row_pitch, ROWB);
-            }
-            if (s + 4 + pf_rows < s_hi) {
-                l2_prefetch_row(pf + rstep, ROWB);
-                if (DOWN2) l2_prefetch_row(pf + rstep + row_pitch, ROWB);
-            }
-        }
-        *reinterpret_cast<uint2 *>(d) = luma8<LAYOUT, DOWN2, NW>(a0, a1);
-        if (s + 8 < s_hi) {
-            load_chunk<BYTES>(p + 2 * rstep, a0);
-            if (DOWN2) load_chunk<BYTES>(p + 2 * rstep + row_pitch, a1);
-        }
-        if (haveB) *reinterpret_cast<uint2 *>(d + 4 * FLP) = luma8<LAYOUT, DOWN2, NW>(b0, b1);
-        s += 8;
-        p += 2 * rstep;
-        pf += 2 * rstep;
-        d += 8 * FLP;
-    }
-}
-
-// Phase F with THREE register sets in rotation (the 8-warp / 128-register variant): the loads of a
-// thread's rows k+1 and k+2 are in flight while row k is converted, so an L2-latency load has two
-// conversions to land.
-template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void front_end3(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
-                                           uint8_t *sL, int pf_mode, int pf_rows) {
-    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
-    constexpr int SPP = DOWN2 ? 2 : 1;
-    constexpr int BYTES = 8 * SPP * CH;
-    constexpr int NW = BYTES / 4;
-    constexpr uint32_t ROWB = BYTES * 64;
-    const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
-    const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
-    for (int s = rsub; s < nL; s += 4) {
-        if (s < s_lo || s >= s_hi) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + col8 * 8) = make_uint2(0u, 0u);
-        if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
-    }
-    uint32_t a0[NW], a1[DOWN2 ? NW : 1], b0[NW], b1[DOWN2 ? NW : 1], c0[NW], c1[DOWN2 ? NW : 1];
-    const size_t rstep = (size_t)(4 * SPP) * row_pitch;
-    int s = s_lo + rsub;
-    const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
-    uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
-    const uint8_t *pf = p + (size_t)(pf_rows * SPP) * row_pitch;
-    const bool pf_on = col8 == 0 && pf_mode >= 1;
-    if (s < s_hi) {
-        load_chunk<BYTES>(p, a0);
-        if (DOWN2) load_chunk<BYTES>(p + row_pitch, a1);
-    }
-    if (s + 4 < s_hi) {
-        load_chunk<BYTES>(p + rstep, b0);
-        if (DOWN2) load_chunk<BYTES>(p + rstep + row_pitch, b1);
-    }
-    while (s < s_hi) {
-        if (s + 8 < s_hi) {
-            load_chunk<BYTES>(p + 2 * rstep, c0);
-            if (DOWN2) load_chunk<BYTES>(p + 2 * rstep + row_pitch, c1);
-        }
-        if (pf_on) {
 #pragma unroll
-            for (int q = 0; q < 3; q++) {
-                if (s + 4 * q + pf_rows < s_hi) {
-                    l2_prefetch_row(pf + q * rstep, ROWB);
-                    if (DOWN2) l2_prefetch_row(pf + q * rstep + row_pitch, ROWB);
+    for (int q = 0; q < SETS - 1; q++) {
+        if (s + 4 * q < s_hi) {
+            load_chunk<BYTES>(p + q * rstep, w0[q]);
+            if (DOWN2) load_chunk<BYTES>(p + q * rstep + row_pitch, w1[q]);
+        }
+    }
+    while (s < s_hi) {
+#pragma unroll
+        for (int q = 0; q < SETS; q++) {
+            constexpr int AHEAD = SETS - 1;
+            const int qa = (q + AHEAD) % SETS;          // the set converted AHEAD sweeps from now
+            if (s + 4 * (q + AHEAD) < s_hi) {
+                load_chunk<BYTES>(p + (q + AHEAD) * rstep, w0[qa]);
+                if (DOWN2) load_chunk<BYTES>(p + (q + AHEAD) * rstep + row_pitch, w1[qa]);
+            }
+            if (q == 0 && pf_on) {
+#pragma unroll
+                for (int u = 0; u < SETS; u++) {
+                    if (s + 4 * u + pf_rows < s_hi) {
+                        l2_prefetch_row(pf + u * rstep, ROWB);
+                        if (DOWN2) l2_prefetch_row(pf + u * rstep + row_pitch, ROWB);
+                    }
                 }
             }
+            if (s + 4 * q < s_hi) *reinterpret_cast<uint2 *>(d + 4 * q * FLP) = luma8<LAYOUT, DOWN2, NW>(w0[q], w1[q]);
         }
-        *reinterpret_cast<uint2 *>(d) = luma8<LAYOUT, DOWN2, NW>(a0, a1);
-        if (s + 12 < s_hi) {
-            load_chunk<BYTES>(p + 3 * rstep, a0);
-            if (DOWN2) load_chunk<BYTES>(p + 3 * rstep + row_pitch, a1);
-        }
-        if (s + 4 < s_hi) *reinterpret_cast<uint2 *>(d + 4 * FLP) = luma8<LAYOUT, DOWN2, NW>(b0, b1);
-        if (s + 16 < s_hi) {
-            load_chunk<BYTES>(p + 4 * rstep, b0);
-            if (DOWN2) load_chunk<BYTES>(p + 4 * rstep + row_pitch, b1);
-        }
-        if (s + 8 < s_hi) *reinterpret_cast<uint2 *>(d + 8 * FLP) = luma8<LAYOUT, DOWN2, NW>(c0, c1);
-        s += 12;
-        p += 3 * rstep;
-        pf += 3 * rstep;
-        d += 12 * FLP;
+        s += 4 * SETS;
+        p += SETS * rstep;
+        pf += SETS * rstep;
+        d += 4 * SETS * FLP;
     }
 }
 
@@ -432,14 +373,24 @@ __device__ __forceinline__ uint32_t window_sum_down(uint32_t h) {
 }
 
 // RN(s / d) for the integer s held in a 16-bit field of `packed` (sel picks the field) and
-// d = 8 cnt (or 4 cnt), y = RN(1/d):  q = f y;  r = fma(-d, q, f);  q' = fma(r, y, q).
-// Equal to IEEE division for every (s <= 16320, cnt <= 8): tools/fused_model.py and
-// tests/test_fused_model.py check the whole set.
-__device__ __forceinline__ float div_exact(uint32_t packed, uint32_t sel, float d, float y) {
-    const float f = __fsub_rn(__uint_as_float(prmt(packed, 0x4B000000u, sel)), 8388608.0f);
-    const float q = __fmul_rn(f, y);
-    const float r = __fmaf_rn(-d, q, f);
-    return __fmaf_rn(r, y, q);
+// d = 8 cnt (or 4 cnt), from a two-term reciprocal: yh = RN(1/d), yl = RN(RN(1 - d yh) yh) ~ 1/d - yh,
+// q = fma(f, yh, RN(f yl)).  f yh + f yl is within 2^-45 of s / d, far inside the 1/6 ulp that
+// separates s / d from a rounding tie, so q equals IEEE division for every (s <= 16320, cnt <= 8):
+// tests/test_fused_model.py checks the whole set.  `magic` is 0x4B000000 held in a register (it
+// comes from the kernel arguments so that the PRMT keeps its selector as the immediate).
+__device__ __forceinline__ float div_exact(uint32_t packed, uint32_t sel, uint32_t magic, float yh, float yl) {
+    const float f = __fsub_rn(__uint_as_float(prmt(packed, magic, sel)), 8388608.0f);
+    return __fmaf_rn(f, yh, __fmul_rn(f, yl));
+}
+
+struct Recip {
+    float h, l;
+};
+__device__ __forceinline__ Recip recip2(float d) {
+    Recip r;
+    r.h = __frcp_rn(d);
+    r.l = __fmul_rn(__fmaf_rn(-d, r.h, 1.0f), r.h);
+    return r;
 }
 
 struct ChainState {
@@ -455,8 +406,8 @@ enum { G_FIRST = 0, G_MID = 1, G_LAST = 2 };
 // One 16-column group of the pass-3 row chain: entering columns e = 16 g - 4 .. 16 g + 11, two per
 // step.  `cur` holds luma columns 16 g .. 16 g + 15 of the lane's row.
 template <int WC, int KIND>
-__device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, float d8, float y8, float d4,
-                                            float y4, const float *p2e, float *p3col, bool store) {
+__device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, uint32_t magic, Recip y8, Recip y4,
+                                            const float *p2e, float *p3col, bool store) {
     const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
     for (int p = 0; p < 8; p++) {
@@ -476,16 +427,16 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
             x1 = p2e[1];
         } else if (KIND == G_FIRST && p == 3) {                // e = 2 inexact, e = 3 exact
             x0 = p2e[2];
-            x1 = div_exact(b, 0x7632u, d8, y8);
+            x1 = div_exact(b, 0x7632u, magic, y8.h, y8.l);
         } else if (KIND == G_LAST && p == 0) {                 // e = 508, 509
             x0 = p2e[3];
             x1 = p2e[4];
         } else if (KIND == G_LAST && p == 1) {                 // e = 510 inexact; e = 511: 4-wide window
             x0 = p2e[5];
-            x1 = div_exact(b, 0x7632u, d4, y4);
+            x1 = div_exact(b, 0x7632u, magic, y4.h, y4.l);
         } else {
-            x0 = div_exact(b, 0x7610u, d8, y8);
-            x1 = div_exact(b, 0x7632u, d8, y8);
+            x0 = div_exact(b, 0x7610u, magic, y8.h, y8.l);
+            x1 = div_exact(b, 0x7632u, magic, y8.h, y8.l);
         }
         // pass-3 chain (pdqhash.rs:366-387): entering column e, leaving e - 8, output column e - 4
         const bool full = !(KIND == G_FIRST && p < 6);         // e >= 8
@@ -507,8 +458,8 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
 // Phase C for one band: lane = row.  Warp w owns luma slots [w OPW, w OPW + 31] of the band window
 // and produces output rows b0 + w OPW + lane for lane < OPW = 33 - WC.
 template <int WC>
-__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_rows, int p2e_first_row, int p2e_nrows,
-                                            float *p3t, int H, int b0, int rows_out, int nL) {
+__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_img, float *p3t, int H, int b0,
+                                            int rows_out, int nL, uint32_t magic) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro = warp * OPW + lane;   // output row within the band == luma slot of the window top
@@ -516,11 +467,9 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     const bool store = lane < OPW && ro < rows_out;
     const int lo = max(0, r - HT), hi = min(H - 1, r + HB);
     const float cnt = (float)max(1, hi - lo + 1);   // rows in the clipped column window
-    const float d8 = 8.0f * cnt, d4 = 4.0f * cnt;
-    const float y8 = __frcp_rn(d8), y4 = __frcp_rn(d4);
+    const Recip y8 = recip2(8.0f * cnt), y4 = recip2(4.0f * cnt);
     const uint8_t *rowp = sL + (size_t)min(ro, nL - 1) * FLP;
-    // edge-column values of plane row r: p2e_rows holds rows [p2e_first_row, p2e_first_row + p2e_nrows)
-    const float *p2e = p2e_rows + (size_t)min(r - p2e_first_row, p2e_nrows - 1) * 6;
+    const float *p2e = p2e_img + (size_t)min(r, H - 1) * 6;   // edge-column values of plane row r (pdq_edge_kernel)
     float *p3col = p3t + r;
     ChainState st;
     st.aprev = 0u;
@@ -530,11 +479,11 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     for (int i = 0; i < 4; i++) st.S[i] = 0u;
 #pragma unroll
     for (int i = 0; i < 8; i++) st.ring[i] = 0.0f;
-    chain_group<WC, G_FIRST>(st, *reinterpret_cast<const uint4 *>(rowp), 0, d8, y8, d4, y4, p2e, p3col, store);
+    chain_group<WC, G_FIRST>(st, *reinterpret_cast<const uint4 *>(rowp), 0, magic, y8, y4, p2e, p3col, store);
 #pragma unroll 1
     for (int g = 1; g < 32; g++)
-        chain_group<WC, G_MID>(st, *reinterpret_cast<const uint4 *>(rowp + 16 * g), g, d8, y8, d4, y4, p2e, p3col, store);
-    chain_group<WC, G_LAST>(st, *reinterpret_cast<const uint4 *>(rowp + FW), 32, d8, y8, d4, y4, p2e, p3col, store);
+        chain_group<WC, G_MID>(st, *reinterpret_cast<const uint4 *>(rowp + 16 * g), g, magic, y8, y4, p2e, p3col, store);
+    chain_group<WC, G_LAST>(st, *reinterpret_cast<const uint4 *>(rowp + FW), 32, magic, y8, y4, p2e, p3col, store);
     // first output of the shrink phase: column 508 = sample 63, window of 7 (pdqhash.rs:389-395).
     // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
     st.sum = __fsub_rn(st.sum, st.ring[4]);
@@ -545,170 +494,206 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
 
 // Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
 // columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
-// memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, all in flight), then
-// threads 0..63 (one per column) walk it at shared-memory latency.
+// memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, P4_UNROLL per thread in
+// flight before the first store), then threads 0..63 (one per column) walk it at shared-memory
+// latency.  The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit stores of the
+// staging and the 128-bit loads of the walk (8 lanes per wavefront) are both conflict-free.
 constexpr int P4_ROWS = 192;
-constexpr int P4_PITCH = P4_ROWS + 1;   // odd pitch: lane j reads bank (j + k) % 32
-static_assert(sizeof(TailSmem) + 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
+constexpr int P4_PITCH = P4_ROWS + 4;
+constexpr int P4_UNROLL = 6;
+static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitch");
+static_assert((64 * (P4_ROWS / 4)) % (FTHREADS * P4_UNROLL) == 0, "pass-4 staging loop has no remainder");
+constexpr size_t P4_STAGE_OFF = (sizeof(TailSmem) + 15) & ~size_t(15);   // 16-byte aligned for the 128-bit accesses
+static_assert(P4_STAGE_OFF + 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
 
-template <int WC>
-__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage) {
-    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
-    const int j = threadIdx.x;
-    float sum = 0.0f, cnt = 0.0f;
-    int i_next = 0, ini = H >> 7;   // ((2 i + 1) H) / 128 for i = 0
-    float prev[8], cur[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-    for (int c0 = 0; c0 < H; c0 += P4_ROWS) {
-        __syncthreads();   // the previous chunk has been consumed
-        for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += blockDim.x) {
-            const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(p3t + (size_t)col * P3_PITCH + c0) + q);
-            float *d = stage + col * P4_PITCH + 4 * q;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-        __syncthreads();
-        if (j < 64) {
-            const float *colp = stage + j * P4_PITCH;
-            const int rows = min(P4_ROWS, H - c0);
-            for (int r0 = 0; r0 < rows; r0 += 8) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) cur[k] = colp[r0 + k];
-                if (c0 + r0 >= 8 && c0 + r0 + 8 <= H) {
-                    // steady state (pdqhash.rs:380-387): every row slides, nothing to clip
-                    // The eight running sums are kept and the (one or two) decimated rows of
-                    // the batch are picked afterwards: no branch inside the dependent add chain.
-                    float sums[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
-                        sum = __fsub_rn(__fadd_rn(sum, cur[k]), old);
-                        sums[k] = sum;
-                    }
-                    const int base = c0 + r0 - HB;   // output row of sums[0]
-                    while (ini < base + 8 && i_next < 64) {
-                        const int k = ini - base;    // >= 0: earlier rows were emitted by earlier batches
-                        float v = sums[0];
-#pragma unroll
-                        for (int q = 1; q < 8; q++) v = (k == q) ? sums[q] : v;
-                        B[i_next * 64 + j] = __fdiv_rn(v, cnt);
-                        i_next++;
-                        ini = ((2 * i_next + 1) * H) >> 7;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int ri = c0 + r0 + k;
-                        if (ri >= H) break;
-                        const float x = cur[k];
-                        bool emit = true;
-                        if (ri < HALF - 1) {
-                            sum = __fadd_rn(sum, x);
-                            cnt += 1.0f;
-                            emit = false;
-                        } else if (ri < WC) {
-                            sum = __fadd_rn(sum, x);
-                            cnt += 1.0f;
-                        } else {
-                            const float old = (k >= WC) ? cur[(k - WC) & 7] : prev[(8 + k - WC) & 7];
-                            sum = __fadd_rn(sum, x);
-                            sum = __fsub_rn(sum, old);
-                        }
-                        if (emit && ri - HB == ini) {
-                            B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
-                            i_next++;
-                            ini = ((2 * i_next + 1) * H) >> 7;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) prev[k] = cur[k];
-            }
+struct PhaseClock {
+    unsigned long long *acc;
+    long long t;
+    __device__ __forceinline__ void start(unsigned long long *p) {
+        acc = p;
+        if (acc != nullptr && threadIdx.x == 0) t = clock64();
+    }
+    // call right after the barrier that ends phase `ph`
+    __device__ __forceinline__ void lap(int ph) {
+        if (acc != nullptr && threadIdx.x == 0) {
+            const long long now = clock64();
+            atomicAdd(acc + ph, (unsigned long long)(now - t));
+            t = now;
         }
     }
-    if (j < 64) {
-        // shrink phase: outputs H-HB .. H-1, leaving rows H-WC ..
-        const float *col = p3t + (size_t)j * P3_PITCH;
-        for (int k = 0; k < HALF - 1; k++) {
-            const float old = __ldcg(col + (H - WC + k));
-            sum = __fsub_rn(sum, old);
-            cnt -= 1.0f;
-            if (H - HB + k == ini && i_next < 64) {
-                B[i_next * 64 + j] = __fdiv_rn(sum, cnt);
-                i_next++;
-                ini = ((2 * i_next + 1) * H) >> 7;
-            }
+};
+
+// Running window sums of pass 4 for one staged chunk, in place: on return colp[i] holds the window
+// sum after plane row c0 + i has entered (= the sum of output row c0 + i - HB).  Nothing but the
+// dependent add / subtract pair per row sits on the chain: decimation and the division by the row
+// count are done afterwards by the whole CTA (p4_gather).
+template <int WC>
+__device__ __forceinline__ void p4_walk(float *colp, int c0, int rows, float &sum, float (&prev)[8]) {
+    float cur[8];
+    int r0 = 0;
+    if (c0 == 0) {   // rows 0 .. 7: the window is still filling for ri < WC (pdqhash.rs:366-378)
+        const float4 lo = *reinterpret_cast<const float4 *>(colp);
+        const float4 hi = *reinterpret_cast<const float4 *>(colp + 4);
+        cur[0] = lo.x; cur[1] = lo.y; cur[2] = lo.z; cur[3] = lo.w;
+        cur[4] = hi.x; cur[5] = hi.y; cur[6] = hi.z; cur[7] = hi.w;
+        float sums[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            sum = __fadd_rn(sum, cur[k]);
+            if (k >= WC) sum = __fsub_rn(sum, cur[k - WC]);
+            sums[k] = sum;
+        }
+        *reinterpret_cast<float4 *>(colp) = make_float4(sums[0], sums[1], sums[2], sums[3]);
+        *reinterpret_cast<float4 *>(colp + 4) = make_float4(sums[4], sums[5], sums[6], sums[7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) prev[k] = cur[k];
+        r0 = 8;
+    }
+    // steady state (pdqhash.rs:380-387); rows past the image in the last batch are computed on
+    // whatever the staging left there and never read
+#pragma unroll 2
+    for (; r0 < rows; r0 += 8) {
+        const float4 lo = *reinterpret_cast<const float4 *>(colp + r0);
+        const float4 hi = *reinterpret_cast<const float4 *>(colp + r0 + 4);
+        cur[0] = lo.x; cur[1] = lo.y; cur[2] = lo.z; cur[3] = lo.w;
+        cur[4] = hi.x; cur[5] = hi.y; cur[6] = hi.z; cur[7] = hi.w;
+        float sums[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float old = (k >= WC) ? cur[k - WC] : prev[8 + k - WC];
+            sum = __fsub_rn(__fadd_rn(sum, cur[k]), old);
+            sums[k] = sum;
+        }
+        *reinterpret_cast<float4 *>(colp + r0) = make_float4(sums[0], sums[1], sums[2], sums[3]);
+        *reinterpret_cast<float4 *>(colp + r0 + 4) = make_float4(sums[4], sums[5], sums[6], sums[7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) prev[k] = cur[k];
+    }
+}
+
+// Decimated rows whose window sum lies in the staged chunk (or in the shrink-phase sums `shr`, for the
+// last HB output rows) -> B, divided by the number of rows in the clipped window (pdqhash.rs:372,
+// :385, :393: the reference divides the running sum by its running count).
+template <int WC>
+__device__ __forceinline__ void p4_gather(const float *stage, const float *shr, int H, int c0, int rows, bool last, float *B) {
+    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1, HT = WC - HALF;
+    const int j = threadIdx.x & 63;
+    for (int i = threadIdx.x >> 6; i < 64; i += FTHREADS / 64) {
+        const int o = ((2 * i + 1) * H) >> 7;   // decimated output row (pdqhash.rs:435)
+        const int src = o + HB - c0;            // staged slot whose sum is output row o
+        const float cnt = (float)(min(o + HB, H - 1) - max(o - HT, 0) + 1);
+        if (o >= H - HB) {
+            if (last) B[i * 64 + j] = __fdiv_rn(shr[(o - (H - HB)) * 64 + j], cnt);
+        } else if (src >= 0 && src < rows) {
+            B[i * 64 + j] = __fdiv_rn(stage[j * P4_PITCH + src], cnt);
         }
     }
 }
 
-template <int LAYOUT, bool DOWN2, int WC, bool EDGEK>
-__global__ void __launch_bounds__(EDGEK ? FWORK : FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
+template <int WC>
+__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, PhaseClock &clk) {
+    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
+    const int j = threadIdx.x;
+    float sum = 0.0f;
+    float prev[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) prev[k] = 0.0f;
+    for (int c0 = 0; c0 < H; c0 += P4_ROWS) {
+        const int rows = min(P4_ROWS, H - c0);
+        const bool last = c0 + P4_ROWS >= H;
+        for (int i0 = threadIdx.x; i0 < 64 * (P4_ROWS / 4); i0 += FTHREADS * P4_UNROLL) {
+            float4 v[P4_UNROLL];
+#pragma unroll
+            for (int u = 0; u < P4_UNROLL; u++) {
+                const int idx = i0 + u * FTHREADS;
+                const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
+                // (rows past H are loaded but never used; the clamp keeps the last chunk inside its column)
+                v[u] = __ldcg(reinterpret_cast<const float4 *>(p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4)));
+            }
+#pragma unroll
+            for (int u = 0; u < P4_UNROLL; u++) {
+                const int idx = i0 + u * FTHREADS;
+                const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
+                *reinterpret_cast<float4 *>(stage + col * P4_PITCH + 4 * q) = v[u];
+            }
+        }
+        // the rows that leave during the shrink phase (H-WC .. H-WC+HB-1), fetched under the walk
+        float leave[HB > 0 ? HB : 1];
+        if (last && j < 64) {
+#pragma unroll
+            for (int k = 0; k < HB; k++) leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
+        }
+        __syncthreads();
+        clk.lap(PH_P4_STAGE);
+        if (j < 64) {
+            p4_walk<WC>(stage + j * P4_PITCH, c0, rows, sum, prev);
+            if (last) {   // shrink phase (pdqhash.rs:389-395): outputs H-HB .. H-1
+                // the walk may have run past row H-1 inside its last batch of 8: restart from the sum of row H-1
+                sum = stage[j * P4_PITCH + rows - 1];
+#pragma unroll
+                for (int k = 0; k < HB; k++) {
+                    sum = __fsub_rn(sum, leave[k]);
+                    shr[k * 64 + j] = sum;
+                }
+            }
+        }
+        __syncthreads();
+        clk.lap(PH_P4_CHAIN);
+        p4_gather<WC>(stage, shr, H, c0, rows, last, B);
+        if (!last) __syncthreads();   // the next chunk overwrites the staging
+    }
+}
+
+template <int LAYOUT, bool DOWN2, int WC>
+__global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sL = smem;
-    float *sE = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);
-    float *sRing = sE + FMAXL * 6;
     TailSmem &ts = *reinterpret_cast<TailSmem *>(smem);   // aliases the luma band, used after the last band
+    float *sD = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);   // DCT matrix, resident for the whole kernel
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, OPW = 33 - WC;
     constexpr int NWC = (FBAND + OPW - 1) / OPW;           // warps that run row chains
-    static_assert(NWC <= 8, "warp 8 is reserved for the edge columns");
+    static_assert(NWC <= FTHREADS / 32, "one warp per OPW output rows of a band");
     const int H = a.H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *p3t = a.p3t + (size_t)blockIdx.x * 64 * P3_PITCH;
+    for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) sD[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
+    PhaseClock clk;
+    clk.start(a.phase_clk);
 
     for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
         const uint8_t *src = a.px + (size_t)img * a.img_pitch;
         const uint8_t *next_src = img + gridDim.x < a.n ? src + (size_t)gridDim.x * a.img_pitch : nullptr;
-        EdgeState est;
-        est.sum = 0.0f;
         for (int b0 = 0; b0 < H; b0 += FBAND) {
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
-            if (EDGEK) {
-                // 8 warps, up to 128 registers: three register sets of loads in flight; the edge
-                // columns were computed by pdq_edge_kernel
-                front_end3<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
-            } else if (warp < 8) {
-                front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
-            } else {   // the edge warp works alongside the front end
-                edge_p1<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sE, lane);
-                __syncwarp();
-                if (lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
-                __syncwarp();
-                edge_divide<WC>(sE, H, b0, rows_out, Lr0, lane);
-            }
+            front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
             __syncthreads();
-            if (warp < NWC) {
-                if (EDGEK)
-                    chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, 0, H, p3t, H, b0, rows_out, nL);
-                else
-                    chain_phase<WC>(sL, sE, Lr0, nL, p3t, H, b0, rows_out, nL);
-            }
+            clk.lap(PH_FRONT);
+            if (warp < NWC) chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, p3t, H, b0, rows_out, nL, a.magic);
             // warm L2 with the first PF_ROWS rows of whatever the front end loads next (the next band
             // of this image, else the first band of the CTA's next image), a few us before it starts
-            if (lane == 0 && warp < 8 && a.pf_mode >= 2) {
+            if (lane == 0 && a.pf_mode >= 2) {
                 if (b0 + FBAND < H)
                     l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND - HT, b0 + FBAND - HT + a.pf_rows, warp, 8);
                 else if (next_src != nullptr)
                     l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, a.pf_rows, warp, 8);
             }
             __syncthreads();
+            clk.lap(PH_CHAIN);
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
-        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + sizeof(TailSmem)));
-        for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) ts.D[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
+        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
         __syncthreads();
-        if (threadIdx.x < FWORK) {   // the tail runs on 256 threads (named barrier 1)
-            const size_t oimg = (size_t)img + (size_t)a.out_offset;
-            const float q = tail_quality(ts);
-            if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
-            tail_dct(ts);
-            if (a.out.coeffs) a.out.coeffs[oimg * 256 + threadIdx.x] = ts.C[threadIdx.x];
-            tail_hashes(ts, a.out, oimg);
-        }
+        clk.lap(PH_P4_STAGE);   // (the last gather)
+        const size_t oimg = (size_t)img + (size_t)a.out_offset;
+        const float q = tail_quality(ts);
+        if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
+        tail_dct(ts, sD);
+        if (a.out.coeffs) a.out.coeffs[oimg * 256 + threadIdx.x] = ts.C[threadIdx.x];
+        tail_hashes(ts, a.out, oimg);
         __syncthreads();   // the next image's front end overwrites the aliased tail scratch
+        clk.lap(PH_TAIL);
     }
 }
 
@@ -749,20 +734,13 @@ __global__ void __launch_bounds__(256) pdq_edge_kernel(const uint8_t *__restrict
 
 template <int LAYOUT, bool DOWN2, int WC>
 int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
-    if (a.p2e != nullptr) {
-        pdq_edge_kernel<LAYOUT, DOWN2, WC><<<cdiv((size_t)a.n, 8), 256, 0, ctx->stream>>>(
-            a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
-        RH_LAUNCHED(ctx, "pdq_edge_kernel");
-        auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC, true>;
-        RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
-        kern<<<grid, FWORK, FSMEM, ctx->stream>>>(a);
-        RH_LAUNCHED(ctx, "pdq_fused_kernel");
-    } else {
-        auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC, false>;
-        RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
-        kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
-        RH_LAUNCHED(ctx, "pdq_fused_kernel");
-    }
+    pdq_edge_kernel<LAYOUT, DOWN2, WC><<<cdiv((size_t)a.n, 8), 256, 0, ctx->stream>>>(
+        a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
+    RH_LAUNCHED(ctx, "pdq_edge_kernel");
+    auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC>;
+    RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
+    kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
+    RH_LAUNCHED(ctx, "pdq_fused_kernel");
     return RH_OK;
 }
 
@@ -796,22 +774,26 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
         return fail(ctx, RH_EINVAL, "fused PDQ kernel: pixels must be 16-byte aligned (pdq_fused_aligned)");
     int grid = ctx->sm_count * 2;
     if (grid > n) grid = (int)n;
-    void *p;
-    RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p));
+    void *p, *p_p3t, *p_p2e;
+    RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p_p3t));
+    RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &p_p2e));
     FusedArgs a;
-    a.p2e = nullptr;
-    const char *ek = getenv("RH_PDQ_EDGE_KERNEL");   // default: 8-warp main kernel + separate edge-column kernel
-    if (!(ek && ek[0] == '0')) {
-        void *pe;
-        RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &pe));
-        a.p2e = (const float *)pe;
+    a.magic = 0x4B000000u;
+    a.p2e = (const float *)p_p2e;
+    // RH_PDQ_PHASE_CLOCKS=1: per-phase cycle totals of thread 0 of every CTA, printed after the kernel
+    const bool clocks = getenv("RH_PDQ_PHASE_CLOCKS") != nullptr;
+    a.phase_clk = nullptr;
+    if (clocks) {
+        RH_TRY(scratch(ctx, S_W8, NPHASE * sizeof(unsigned long long), &p));
+        a.phase_clk = (unsigned long long *)p;
+        RH_CUDA(ctx, cudaMemsetAsync(p, 0, NPHASE * sizeof(unsigned long long), ctx->stream));
     }
     a.px = d_px;
     a.row_pitch = row_pitch;
     a.img_pitch = img_pitch;
     a.n = n;
     a.H = H;
-    a.p3t = (float *)p;
+    a.p3t = (float *)p_p3t;
     a.dct = d_dct;
     a.out = out;
     a.out_offset = out_offset;
@@ -820,11 +802,26 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     const char *pfr = getenv("RH_PDQ_PREFETCH_ROWS");
     a.pf_rows = pfr ? atoi(pfr) : PF_ROWS;
     const int wc = (H + 63) / 64;
+    int rc;
     if (layout == RH_LAYOUT_RGB8)
-        return down2 ? dispatch_wc<RH_LAYOUT_RGB8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGB8, false>(ctx, a, grid, wc);
-    if (layout == RH_LAYOUT_RGBA8)
-        return down2 ? dispatch_wc<RH_LAYOUT_RGBA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGBA8, false>(ctx, a, grid, wc);
-    return down2 ? dispatch_wc<RH_LAYOUT_LUMA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_LUMA8, false>(ctx, a, grid, wc);
+        rc = down2 ? dispatch_wc<RH_LAYOUT_RGB8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGB8, false>(ctx, a, grid, wc);
+    else if (layout == RH_LAYOUT_RGBA8)
+        rc = down2 ? dispatch_wc<RH_LAYOUT_RGBA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_RGBA8, false>(ctx, a, grid, wc);
+    else
+        rc = down2 ? dispatch_wc<RH_LAYOUT_LUMA8, true>(ctx, a, grid, wc) : dispatch_wc<RH_LAYOUT_LUMA8, false>(ctx, a, grid, wc);
+    if (rc == RH_OK && clocks) {
+        unsigned long long h[NPHASE];
+        RH_CUDA(ctx, cudaMemcpyAsync(h, a.phase_clk, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        static const char *names[NPHASE] = {"front", "chain", "p4_stage", "p4_chain", "tail"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < NPHASE; i++) tot += h[i];
+        fprintf(stderr, "[pdq_fused phases] n=%lld", (long long)n);
+        for (int i = 0; i < NPHASE; i++)
+            fprintf(stderr, "  %s %.0f cyc/img (%.1f%%)", names[i], (double)h[i] / (double)n, 100.0 * (double)h[i] / (double)tot);
+        fprintf(stderr, "\n");
+    }
+    return rc;
 }
 
 }  // namespace rh

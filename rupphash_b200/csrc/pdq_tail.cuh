@@ -13,7 +13,7 @@ namespace rh {
 constexpr int TAIL_THREADS = 256;
 
 // The tail synchronises on named barrier 1 over exactly TAIL_THREADS threads, so that a kernel
-// with extra warps (pdq_fused_kernel's edge warp) can run it on its first 256 threads only.
+// with extra warps can run it on its first 256 threads only.
 __device__ __forceinline__ void tail_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ int tail_count(bool pred) {
     int n;
@@ -125,6 +125,7 @@ __device__ __forceinline__ void tail_hashes(TailSmem &s, const TailOut &o, size_
 // the identical value.  Needs s.B; all threads must call; result valid in thread 0.
 __device__ __forceinline__ float tail_quality(TailSmem &s) {
     int acc = 0;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < 4096; idx += TAIL_THREADS) {
         const int i = idx >> 6, j = idx & 63;
         const float a = s.B[idx];
@@ -152,8 +153,9 @@ __device__ __forceinline__ float tail_quality(TailSmem &s) {
     return q;
 }
 
-// pdqhash.rs:306-336 with s.B and s.D loaded; leaves the coefficients in s.C.
-__device__ __forceinline__ void tail_dct(TailSmem &s) {
+// pdqhash.rs:306-336 with s.B loaded and the DCT matrix (16 rows of pitch DCT_PITCH, shared memory)
+// at D; leaves the coefficients in s.C.
+__device__ __forceinline__ void tail_dct(TailSmem &s, const float *D) {
     {   // T[i][j] = sum_k D[i][k] * B[k][j], k ascending from 0.0
         const int j = threadIdx.x & 63, i0 = (threadIdx.x >> 6) * 4;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -161,7 +163,7 @@ __device__ __forceinline__ void tail_dct(TailSmem &s) {
         for (int k = 0; k < 64; k++) {
             const float b = s.B[k * 64 + j];
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(s.D[(i0 + u) * DCT_PITCH + k], b));
+            for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(D[(i0 + u) * DCT_PITCH + k], b));
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) s.T[(i0 + u) * 64 + j] = acc[u];
@@ -171,7 +173,7 @@ __device__ __forceinline__ void tail_dct(TailSmem &s) {
         const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
         float acc = 0.f;
 #pragma unroll 8
-        for (int k = 0; k < 64; k++) acc = __fadd_rn(acc, __fmul_rn(s.T[i * 64 + k], s.D[j * DCT_PITCH + k]));
+        for (int k = 0; k < 64; k++) acc = __fadd_rn(acc, __fmul_rn(s.T[i * 64 + k], D[j * DCT_PITCH + k]));
         s.C[threadIdx.x] = acc;
     }
     tail_sync();

@@ -1,5 +1,5 @@
 """CPU proofs behind the fused PDQ kernel (rupphash_b200/csrc/pdq_fused.cu):
-  * the FMA-corrected division it uses equals IEEE f32 division on the whole finite input set;
+  * the two-term-reciprocal division it uses equals IEEE f32 division on the whole finite input set;
   * the restructured algorithm (integer 2-D box sums + one rounding, real chains only where the
     data is inexact) reproduces the oracle's 64x64 buffer bit for bit."""
 import os
@@ -34,17 +34,22 @@ def _rn(v: Fraction) -> np.float32:
 
 @pytest.mark.parametrize("cnt", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_fma_division_equals_ieee_division(cnt):
+    """div_exact / recip2 of pdq_fused.cu: yh = RN(1/d), yl = RN(RN(1 - d yh) yh),
+    q = fma(f, yh, RN(f yl)) against IEEE division, every step in exact rational arithmetic."""
     for scale, smax in ((8, 8 * 8 * 255), (4, 8 * 4 * 255)):
         d = f32(scale * cnt)
-        y = f32(f32(1) / d)
+        yh = f32(f32(1) / d)                                                 # __frcp_rn
+        r = _rn(Fraction(1) - Fraction(float(d)) * Fraction(float(yh)))      # fma(-d, yh, 1)
+        yl = _rn(Fraction(float(r)) * Fraction(float(yh)))
         s = np.arange(0, smax + 1)
         want = (s.astype(f32) / d).astype(f32)
-        q = (s.astype(np.float64) * np.float64(y)).astype(f32)           # exact product, one rounding
-        step = 1 if cnt in (3, 5, 6, 7) else 97
-        for k in range(0, smax + 1, step):
-            fq = Fraction(float(q[k]))
-            r = _rn(Fraction(k) - Fraction(float(d)) * fq)
-            got = _rn(Fraction(float(r)) * Fraction(float(y)) + fq)
+        # vectorised: f yh is exact in f64 (48 bits), t = RN(f yl) has 24; the sum spans < 53 bits
+        t = (s.astype(np.float64) * np.float64(yl)).astype(f32)
+        q = (s.astype(np.float64) * np.float64(yh) + t.astype(np.float64)).astype(f32)
+        assert np.array_equal(q, want), (cnt, scale)
+        for k in range(0, smax + 1, 61):                                     # the same through Fractions
+            tk = _rn(Fraction(k) * Fraction(float(yl)))
+            got = _rn(Fraction(k) * Fraction(float(yh)) + Fraction(float(tk)))
             assert got == want[k], (cnt, scale, k)
 
 

@@ -10,7 +10,8 @@ jarosz_filter_float (pdqhash.rs:410-426) when the row window is 8 (plane width 4
   3. passes 3 and 4 are genuinely sequential float chains and are run as written, but only the
      64 decimated columns of pass 3 feed pass 4.
 The six edge columns get the real sequential column chain.  This script verifies 1-3 and the
-FMA-based division used on the device (q = f*y; r = fma(-d,q,f); q' = fma(r,y,q)).
+FMA-based division first used on the device (q = f*y; r = fma(-d,q,f); q' = fma(r,y,q)); the kernel
+now uses the cheaper two-term reciprocal that tests/test_fused_model.py proves equal as well.
 """
 import os
 import sys
