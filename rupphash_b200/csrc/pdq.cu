@@ -415,7 +415,9 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
                                : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
-    int64_t chunk = fused ? 2048 : 256;
+    // (device-resident input to the fused kernel needs 9 KB of scratch per image: one launch for up
+    // to 16384 images, so that the persistent CTAs see a long queue)
+    int64_t chunk = fused ? (on_device ? 16384 : 2048) : 256;
     if (resize) {   // full-resolution luma + the horizontally resized plane live in scratch
         int64_t c3 = (int64_t)((size_t(1) << 30) / ((size_t)w * h + (size_t)W * h + (size_t)W * H));
         if (c3 < 1) c3 = 1;
