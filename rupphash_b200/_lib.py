@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "librupphash_b200.so")
+SO_PATH = os.environ.get("RH_B200_LIB") or os.path.join(_HERE, "librupphash_b200.so")   # RH_B200_LIB: A/B builds
 
 RH_OK, RH_EINVAL, RH_ECUDA, RH_ENOMEM, RH_EUNSUPPORTED = 0, -1, -2, -3, -4
 LAYOUT_RGB8, LAYOUT_RGBA8, LAYOUT_LUMA8 = 0, 1, 2

@@ -181,8 +181,10 @@ __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row
 // survives only ~30 us in the 126 MB L2).
 // Slots whose plane row lies outside the image (top of the first band, bottom of the last) are
 // stored as zeros, and so are the 16 pad bytes of every row: the chain phase needs no clipping.
-template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
+// PACKED: rows are contiguous (row_pitch == ROWB), so every address in the loop is the thread's
+// pointer plus an immediate -- no pitch multiplies, no reloads of the pitch from the constant bank.
+template <int LAYOUT, bool DOWN2, bool PACKED>
+__device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch_arg, int H, int Lr0, int nL,
                                           uint8_t *sL, int pf_mode, int pf_rows) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
@@ -190,6 +192,7 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     constexpr int NW = BYTES / 4;
     constexpr int SETS = NW * SPP * 3 <= 72 ? 3 : 2;
     constexpr uint32_t ROWB = BYTES * 64;
+    const size_t row_pitch = PACKED ? (size_t)ROWB : row_pitch_arg;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
     const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
     for (int s = rsub; s < nL; s += 4) {
@@ -201,9 +204,7 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     int s = s_lo + rsub;
     const uint8_t *p = src + (size_t)((Lr0 + s) * SPP) * row_pitch + (size_t)col8 * BYTES;
     uint8_t *d = sL + (size_t)s * FLP + col8 * 8;
-    // the prefetch front of this thread (col8 == 0 only): its own rows, pf_rows ahead, inside the band
-    const uint8_t *pf = p + (size_t)(pf_rows * SPP) * row_pitch;
-    const bool pf_on = col8 == 0 && pf_mode >= 1;
+    const bool pf_on = PACKED && (threadIdx.x & 31) == 0 && pf_mode >= 1;
 #pragma unroll
     for (int q = 0; q < SETS - 1; q++) {
         if (s + 4 * q < s_hi) {
@@ -221,19 +222,19 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
                 if (DOWN2) load_chunk<BYTES>(p + (q + AHEAD) * rstep + row_pitch, w1[qa]);
             }
             if (q == 0 && pf_on) {
-#pragma unroll
-                for (int u = 0; u < SETS; u++) {
-                    if (s + 4 * u + pf_rows < s_hi) {
-                        l2_prefetch_row(pf + u * rstep, ROWB);
-                        if (DOWN2) l2_prefetch_row(pf + u * rstep + row_pitch, ROWB);
-                    }
-                }
+                // PACKED rows are contiguous in memory: the 4 SETS plane rows of the sweep group pf_rows
+                // ahead are one byte range; lane 0 of each of the 8 warps prefetches an eighth of it
+                const int f0 = s - rsub + pf_rows, f1 = min(f0 + 4 * SETS, s_hi);
+                constexpr uint32_t PIECE = (uint32_t)(4 * SETS * SPP) * ROWB / 8;
+                static_assert(PIECE % 16 == 0, "bulk prefetch granularity");
+                const int beg = ((Lr0 + f0) * SPP) * (int)ROWB + (int)(threadIdx.x >> 5) * (int)PIECE;
+                const int end = ((Lr0 + f1) * SPP) * (int)ROWB;
+                if (beg < end) l2_prefetch_row(src + beg, (uint32_t)min((int)PIECE, end - beg));
             }
             if (s + 4 * q < s_hi) *reinterpret_cast<uint2 *>(d + 4 * q * FLP) = luma8<LAYOUT, DOWN2, NW>(w0[q], w1[q]);
         }
         s += 4 * SETS;
         p += SETS * rstep;
-        pf += SETS * rstep;
         d += 4 * SETS * FLP;
     }
 }
@@ -479,11 +480,17 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     for (int i = 0; i < 4; i++) st.S[i] = 0u;
 #pragma unroll
     for (int i = 0; i < 8; i++) st.ring[i] = 0.0f;
-    chain_group<WC, G_FIRST>(st, *reinterpret_cast<const uint4 *>(rowp), 0, magic, y8, y4, p2e, p3col, store);
+    // the 16 luma bytes of group g + 1 are fetched while group g runs (no LDS latency on the chain)
+    uint4 cur = *reinterpret_cast<const uint4 *>(rowp);
+    uint4 nxt = *reinterpret_cast<const uint4 *>(rowp + 16);
+    chain_group<WC, G_FIRST>(st, cur, 0, magic, y8, y4, p2e, p3col, store);
 #pragma unroll 1
-    for (int g = 1; g < 32; g++)
-        chain_group<WC, G_MID>(st, *reinterpret_cast<const uint4 *>(rowp + 16 * g), g, magic, y8, y4, p2e, p3col, store);
-    chain_group<WC, G_LAST>(st, *reinterpret_cast<const uint4 *>(rowp + FW), 32, magic, y8, y4, p2e, p3col, store);
+    for (int g = 1; g < 32; g++) {
+        cur = nxt;
+        nxt = *reinterpret_cast<const uint4 *>(rowp + 16 * g + 16);   // g = 31: the zero pad at column 512
+        chain_group<WC, G_MID>(st, cur, g, magic, y8, y4, p2e, p3col, store);
+    }
+    chain_group<WC, G_LAST>(st, nxt, 32, magic, y8, y4, p2e, p3col, store);
     // first output of the shrink phase: column 508 = sample 63, window of 7 (pdqhash.rs:389-395).
     // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
     st.sum = __fsub_rn(st.sum, st.ring[4]);
@@ -495,12 +502,12 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
 // Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
 // columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
 // memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, P4_UNROLL per thread in
-// flight before the first store), then threads 0..63 (one per column) walk it at shared-memory
+// flight before the first store; keeping all 12 in registers spills and costs 8 % of the kernel), then threads 0..63 (one per column) walk it at shared-memory
 // latency.  The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit stores of the
 // staging and the 128-bit loads of the walk (8 lanes per wavefront) are both conflict-free.
 constexpr int P4_ROWS = 192;
 constexpr int P4_PITCH = P4_ROWS + 4;
-constexpr int P4_UNROLL = 6;
+constexpr int P4_UNROLL = 3;
 static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitch");
 static_assert((64 * (P4_ROWS / 4)) % (FTHREADS * P4_UNROLL) == 0, "pass-4 staging loop has no remainder");
 constexpr size_t P4_STAGE_OFF = (sizeof(TailSmem) + 15) & ~size_t(15);   // 16-byte aligned for the 128-bit accesses
@@ -551,7 +558,7 @@ __device__ __forceinline__ void p4_walk(float *colp, int c0, int rows, float &su
     }
     // steady state (pdqhash.rs:380-387); rows past the image in the last batch are computed on
     // whatever the staging left there and never read
-#pragma unroll 2
+#pragma unroll 1
     for (; r0 < rows; r0 += 8) {
         const float4 lo = *reinterpret_cast<const float4 *>(colp + r0);
         const float4 hi = *reinterpret_cast<const float4 *>(colp + r0 + 4);
@@ -578,8 +585,11 @@ template <int WC>
 __device__ __forceinline__ void p4_gather(const float *stage, const float *shr, int H, int c0, int rows, bool last, float *B) {
     constexpr int HALF = (WC + 2) / 2, HB = HALF - 1, HT = WC - HALF;
     const int j = threadIdx.x & 63;
-    for (int i = threadIdx.x >> 6; i < 64; i += FTHREADS / 64) {
+    // first output whose window sum can lie in this chunk: o + HB >= c0  <=  (2 i + 1) H >= 128 (c0 - HB)
+    const int i_lo = max(0, (128 * (c0 - HB) - H) / (2 * H));
+    for (int i = i_lo + (threadIdx.x >> 6); i < 64; i += FTHREADS / 64) {
         const int o = ((2 * i + 1) * H) >> 7;   // decimated output row (pdqhash.rs:435)
+        if (!last && o + HB - c0 >= rows) break;   // the rest belongs to later chunks
         const int src = o + HB - c0;            // staged slot whose sum is output row o
         const float cnt = (float)(min(o + HB, H - 1) - max(o - HT, 0) + 1);
         if (o >= H - HB) {
@@ -644,7 +654,7 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     }
 }
 
-template <int LAYOUT, bool DOWN2, int WC>
+template <int LAYOUT, bool DOWN2, int WC, bool PACKED>
 __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sL = smem;
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
-            front_end<LAYOUT, DOWN2>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
+            front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
             __syncthreads();
             clk.lap(PH_FRONT);
             if (warp < NWC) chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, p3t, H, b0, rows_out, nL, a.magic);
@@ -737,7 +747,9 @@ int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
     pdq_edge_kernel<LAYOUT, DOWN2, WC><<<cdiv((size_t)a.n, 8), 256, 0, ctx->stream>>>(
         a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
     RH_LAUNCHED(ctx, "pdq_edge_kernel");
-    auto kern = pdq_fused_kernel<LAYOUT, DOWN2, WC>;
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    const bool packed = a.row_pitch == (size_t)FW * (DOWN2 ? 2 : 1) * CH;
+    auto kern = packed ? pdq_fused_kernel<LAYOUT, DOWN2, WC, true> : pdq_fused_kernel<LAYOUT, DOWN2, WC, false>;
     RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
     kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
     RH_LAUNCHED(ctx, "pdq_fused_kernel");
