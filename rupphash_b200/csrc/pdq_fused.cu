@@ -63,7 +63,6 @@ struct FusedArgs {
     int64_t out_offset;
     int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
     int pf_rows;       // plane rows between the prefetch front and the loads
-    uint32_t magic;    // 0x4B000000 (bits of 2^23), passed in so that it lives in a register: div_exact
     unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
 };
 
@@ -373,14 +372,15 @@ __device__ __forceinline__ uint32_t window_sum_down(uint32_t h) {
     return a4 + __shfl_down_sync(FULL, a4, 4);
 }
 
-// RN(s / d) for the integer s held in a 16-bit field of `packed` (sel picks the field) and
+// RN(s / d) for the integer s held in the low (HI = false) or high 16-bit field of `packed` and
 // d = 8 cnt (or 4 cnt), from a two-term reciprocal: yh = RN(1/d), yl = RN(RN(1 - d yh) yh) ~ 1/d - yh,
 // q = fma(f, yh, RN(f yl)).  f yh + f yl is within 2^-45 of s / d, far inside the 1/6 ulp that
 // separates s / d from a rounding tie, so q equals IEEE division for every (s <= 16320, cnt <= 8):
-// tests/test_fused_model.py checks the whole set.  `magic` is 0x4B000000 held in a register (it
-// comes from the kernel arguments so that the PRMT keeps its selector as the immediate).
-__device__ __forceinline__ float div_exact(uint32_t packed, uint32_t sel, uint32_t magic, float yh, float yl) {
-    const float f = __fsub_rn(__uint_as_float(prmt(packed, magic, sel)), 8388608.0f);
+// tests/test_fused_model.py checks the whole set.  The conversion is one I2F.U16 with a half-word
+// selector: it runs on the otherwise idle XU pipe instead of a PRMT + FADD pair on the busy ones.
+template <bool HI>
+__device__ __forceinline__ float div_exact(uint32_t packed, float yh, float yl) {
+    const float f = __uint2float_rn(HI ? (packed >> 16) : (packed & 0xFFFFu));
     return __fmaf_rn(f, yh, __fmul_rn(f, yl));
 }
 
@@ -407,7 +407,7 @@ enum { G_FIRST = 0, G_MID = 1, G_LAST = 2 };
 // One 16-column group of the pass-3 row chain: entering columns e = 16 g - 4 .. 16 g + 11, two per
 // step.  `cur` holds luma columns 16 g .. 16 g + 15 of the lane's row.
 template <int WC, int KIND>
-__device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, uint32_t magic, Recip y8, Recip y4,
+__device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, Recip y8, Recip y4,
                                             const float *p2e, float *p3col, bool store) {
     const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
@@ -428,16 +428,16 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
             x1 = p2e[1];
         } else if (KIND == G_FIRST && p == 3) {                // e = 2 inexact, e = 3 exact
             x0 = p2e[2];
-            x1 = div_exact(b, 0x7632u, magic, y8.h, y8.l);
+            x1 = div_exact<true>(b, y8.h, y8.l);
         } else if (KIND == G_LAST && p == 0) {                 // e = 508, 509
             x0 = p2e[3];
             x1 = p2e[4];
         } else if (KIND == G_LAST && p == 1) {                 // e = 510 inexact; e = 511: 4-wide window
             x0 = p2e[5];
-            x1 = div_exact(b, 0x7632u, magic, y4.h, y4.l);
+            x1 = div_exact<true>(b, y4.h, y4.l);
         } else {
-            x0 = div_exact(b, 0x7610u, magic, y8.h, y8.l);
-            x1 = div_exact(b, 0x7632u, magic, y8.h, y8.l);
+            x0 = div_exact<false>(b, y8.h, y8.l);
+            x1 = div_exact<true>(b, y8.h, y8.l);
         }
         // pass-3 chain (pdqhash.rs:366-387): entering column e, leaving e - 8, output column e - 4
         const bool full = !(KIND == G_FIRST && p < 6);         // e >= 8
@@ -460,7 +460,7 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
 // and produces output rows b0 + w OPW + lane for lane < OPW = 33 - WC.
 template <int WC>
 __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_img, float *p3t, int H, int b0,
-                                            int rows_out, int nL, uint32_t magic) {
+                                            int rows_out, int nL) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro = warp * OPW + lane;   // output row within the band == luma slot of the window top
@@ -483,14 +483,14 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     // the 16 luma bytes of group g + 1 are fetched while group g runs (no LDS latency on the chain)
     uint4 cur = *reinterpret_cast<const uint4 *>(rowp);
     uint4 nxt = *reinterpret_cast<const uint4 *>(rowp + 16);
-    chain_group<WC, G_FIRST>(st, cur, 0, magic, y8, y4, p2e, p3col, store);
+    chain_group<WC, G_FIRST>(st, cur, 0, y8, y4, p2e, p3col, store);
 #pragma unroll 1
     for (int g = 1; g < 32; g++) {
         cur = nxt;
         nxt = *reinterpret_cast<const uint4 *>(rowp + 16 * g + 16);   // g = 31: the zero pad at column 512
-        chain_group<WC, G_MID>(st, cur, g, magic, y8, y4, p2e, p3col, store);
+        chain_group<WC, G_MID>(st, cur, g, y8, y4, p2e, p3col, store);
     }
-    chain_group<WC, G_LAST>(st, nxt, 32, magic, y8, y4, p2e, p3col, store);
+    chain_group<WC, G_LAST>(st, nxt, 32, y8, y4, p2e, p3col, store);
     // first output of the shrink phase: column 508 = sample 63, window of 7 (pdqhash.rs:389-395).
     // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
     st.sum = __fsub_rn(st.sum, st.ring[4]);
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
             __syncthreads();
             clk.lap(PH_FRONT);
-            if (warp < NWC) chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, p3t, H, b0, rows_out, nL, a.magic);
+            if (warp < NWC) chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, p3t, H, b0, rows_out, nL);
             // warm L2 with the first PF_ROWS rows of whatever the front end loads next (the next band
             // of this image, else the first band of the CTA's next image), a few us before it starts
             if (lane == 0 && a.pf_mode >= 2) {
@@ -790,7 +790,6 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p_p3t));
     RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &p_p2e));
     FusedArgs a;
-    a.magic = 0x4B000000u;
     a.p2e = (const float *)p_p2e;
     // RH_PDQ_PHASE_CLOCKS=1: per-phase cycle totals of thread 0 of every CTA, printed after the kernel
     const bool clocks = getenv("RH_PDQ_PHASE_CLOCKS") != nullptr;
