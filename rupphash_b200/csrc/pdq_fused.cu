@@ -501,17 +501,25 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
 
 // Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
 // columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
-// memory P4_ROWS rows at a time by the whole CTA (coalesced 128-bit loads, P4_UNROLL per thread in
-// flight before the first store; keeping all 12 in registers spills and costs 8 % of the kernel), then threads 0..63 (one per column) walk it at shared-memory
-// latency.  The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit stores of the
-// staging and the 128-bit loads of the walk (8 lanes per wavefront) are both conflict-free.
-constexpr int P4_ROWS = 192;
+// memory P4_ROWS rows at a time with cp.async (16 bytes per request, no registers, every request of a
+// chunk in flight at once) into two buffers: chunk c + 1 lands while threads 0..63 (one per column)
+// walk chunk c at shared-memory latency, so only the first chunk's L2 round trip is exposed.
+// The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit accesses of the walk (8 lanes
+// per wavefront) are conflict-free.
+constexpr int P4_ROWS = 128;
 constexpr int P4_PITCH = P4_ROWS + 4;
-constexpr int P4_UNROLL = 3;
 static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitch");
-static_assert((64 * (P4_ROWS / 4)) % (FTHREADS * P4_UNROLL) == 0, "pass-4 staging loop has no remainder");
+static_assert((64 * (P4_ROWS / 4)) % FTHREADS == 0 && P4_ROWS % 8 == 0, "pass-4 staging has no remainder");
 constexpr size_t P4_STAGE_OFF = (sizeof(TailSmem) + 15) & ~size_t(15);   // 16-byte aligned for the 128-bit accesses
-static_assert(P4_STAGE_OFF + 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
+static_assert(P4_STAGE_OFF + 2 * 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct PhaseClock {
     unsigned long long *acc;
@@ -600,6 +608,17 @@ __device__ __forceinline__ void p4_gather(const float *stage, const float *shr, 
     }
 }
 
+// plane rows [c0, c0 + P4_ROWS) of the 64 columns -> stg (rows past H are copied but never used;
+// the clamp keeps the last chunk inside its column)
+__device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg) {
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
+        const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
+        cp_async16(stg + col * P4_PITCH + 4 * q, p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4));
+    }
+    cp_async_commit();
+}
+
 template <int WC>
 __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, PhaseClock &clk) {
     constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
@@ -608,38 +627,30 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     float prev[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-    for (int c0 = 0; c0 < H; c0 += P4_ROWS) {
+    p4_issue(p3t, 0, stage);
+    if (P4_ROWS < H) p4_issue(p3t, P4_ROWS, stage + 64 * P4_PITCH);
+    int buf = 0;
+    for (int c0 = 0; c0 < H; c0 += P4_ROWS, buf ^= 1) {
+        float *stg = stage + buf * (64 * P4_PITCH);
         const int rows = min(P4_ROWS, H - c0);
         const bool last = c0 + P4_ROWS >= H;
-        for (int i0 = threadIdx.x; i0 < 64 * (P4_ROWS / 4); i0 += FTHREADS * P4_UNROLL) {
-            float4 v[P4_UNROLL];
-#pragma unroll
-            for (int u = 0; u < P4_UNROLL; u++) {
-                const int idx = i0 + u * FTHREADS;
-                const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
-                // (rows past H are loaded but never used; the clamp keeps the last chunk inside its column)
-                v[u] = __ldcg(reinterpret_cast<const float4 *>(p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4)));
-            }
-#pragma unroll
-            for (int u = 0; u < P4_UNROLL; u++) {
-                const int idx = i0 + u * FTHREADS;
-                const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
-                *reinterpret_cast<float4 *>(stage + col * P4_PITCH + 4 * q) = v[u];
-            }
-        }
         // the rows that leave during the shrink phase (H-WC .. H-WC+HB-1), fetched under the walk
         float leave[HB > 0 ? HB : 1];
         if (last && j < 64) {
 #pragma unroll
             for (int k = 0; k < HB; k++) leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
         }
+        if (last)
+            cp_async_wait<0>();
+        else
+            cp_async_wait<1>();   // everything but the chunk after this one has landed
         __syncthreads();
         clk.lap(PH_P4_STAGE);
         if (j < 64) {
-            p4_walk<WC>(stage + j * P4_PITCH, c0, rows, sum, prev);
+            p4_walk<WC>(stg + j * P4_PITCH, c0, rows, sum, prev);
             if (last) {   // shrink phase (pdqhash.rs:389-395): outputs H-HB .. H-1
                 // the walk may have run past row H-1 inside its last batch of 8: restart from the sum of row H-1
-                sum = stage[j * P4_PITCH + rows - 1];
+                sum = stg[j * P4_PITCH + rows - 1];
 #pragma unroll
                 for (int k = 0; k < HB; k++) {
                     sum = __fsub_rn(sum, leave[k]);
@@ -649,8 +660,11 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
         }
         __syncthreads();
         clk.lap(PH_P4_CHAIN);
-        p4_gather<WC>(stage, shr, H, c0, rows, last, B);
-        if (!last) __syncthreads();   // the next chunk overwrites the staging
+        p4_gather<WC>(stg, shr, H, c0, rows, last, B);
+        if (c0 + 2 * P4_ROWS < H) {   // this buffer takes the chunk after the next one
+            __syncthreads();
+            p4_issue(p3t, c0 + 2 * P4_ROWS, stg);
+        }
     }
 }
 
