@@ -566,12 +566,16 @@ __device__ __forceinline__ void p4_walk(float *colp, int c0, int rows, float &su
     }
     // steady state (pdqhash.rs:380-387); rows past the image in the last batch are computed on
     // whatever the staging left there and never read
+    // (the next batch is loaded before the current one is summed: no LDS latency between batches; the
+    // read one batch past the chunk stays inside the staging area)
+    float4 lo = *reinterpret_cast<const float4 *>(colp + r0);
+    float4 hi = *reinterpret_cast<const float4 *>(colp + r0 + 4);
 #pragma unroll 1
     for (; r0 < rows; r0 += 8) {
-        const float4 lo = *reinterpret_cast<const float4 *>(colp + r0);
-        const float4 hi = *reinterpret_cast<const float4 *>(colp + r0 + 4);
         cur[0] = lo.x; cur[1] = lo.y; cur[2] = lo.z; cur[3] = lo.w;
         cur[4] = hi.x; cur[5] = hi.y; cur[6] = hi.z; cur[7] = hi.w;
+        lo = *reinterpret_cast<const float4 *>(colp + r0 + 8);
+        hi = *reinterpret_cast<const float4 *>(colp + r0 + 12);
         float sums[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
