@@ -16,8 +16,8 @@
 // The six inexact columns get the reference's real column chain (one lane each).
 //
 // Data flow.  pdq_edge_kernel first runs the six inexact columns of every image of the chunk
-// (one warp per image; it reads the first / last 48 source bytes of each row, ~4 % of the pixels)
-// and leaves their pass-2 values in a [n][H][6] scratch.  Then, per image (one CTA, 8 warps,
+// (one 128-thread CTA per image; it reads the first / last 48 source bytes of each row, ~4 % of the
+// pixels) and leaves their pass-2 values in a [n][H][6] scratch.  Then, per image (one CTA, 8 warps,
 // ~108 KB shared memory, 2 CTAs per SM, <= 128 registers so the row chains keep their state in
 // registers):
 //   for each band of 192 rows:
@@ -240,22 +240,18 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
 
 // ---------------------------------------------------------------- edge columns ----
 
-// Edge columns, step 1 (edge warp, lane = plane row): pass-1 values of the six columns whose
-// clipped row window is 5, 6 or 7 wide (box_one_d_float phases 2 and 4, pdqhash.rs:372-378,
-// :389-395) -- rounded quotients.  The edge warp reads the first and last 8-pixel chunk of each
-// row straight from global memory (the same lines the front-end warps fetch at about the same
-// time, so they come from L2) and therefore needs nothing from the other warps: the whole edge
-// pipeline runs concurrently with the front end.
-template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t row_pitch, int H, int Lr0, int nL,
-                                        float *sE, int lane) {
+// Edge columns, step 1 (one thread per plane row, STRIDE threads): pass-1 values of the six columns
+// whose clipped row window is 5, 6 or 7 wide (box_one_d_float phases 2 and 4, pdqhash.rs:372-378,
+// :389-395) -- rounded quotients -- from the first and last 8-pixel chunk of each row, read
+// straight from global memory.  Output is column-major: sE[c * EDGE_PITCH + row].
+constexpr int EDGE_PITCH = 512 + 16;   // rows of a column + one walk batch of read-ahead, 16-byte aligned
+template <int LAYOUT, bool DOWN2, int STRIDE>
+__device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t row_pitch, int H, float *sE, int lane) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;
     constexpr int NW = BYTES / 4;
-    for (int s = lane; s < nL; s += 32) {
-        const int lr = Lr0 + s;
-        if (lr < 0 || lr >= H) continue;
+    for (int lr = lane; lr < H; lr += STRIDE) {
         uint32_t l0[NW], l1[DOWN2 ? NW : 1], r0[NW], r1[DOWN2 ? NW : 1];
         const uint8_t *pl = src + (size_t)(lr * SPP) * row_pitch;
         const uint8_t *pr = pl + (size_t)63 * BYTES;
@@ -275,80 +271,13 @@ __device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t 
         const int t5 = (int)__dp4a(vr.y, 0x01010101u, 0u) + (int)(vr.x >> 24);
         const int t6 = t5 + (int)((vr.x >> 16) & 0xFFu);
         const int t7 = t6 + (int)((vr.x >> 8) & 0xFFu);
-        float *o = sE + s * 6;
-        o[0] = __fdiv_rn((float)s5, 5.0f);
-        o[1] = __fdiv_rn((float)s6, 6.0f);
-        o[2] = __fdiv_rn((float)s7, 7.0f);
-        o[3] = __fdiv_rn((float)t7, 7.0f);
-        o[4] = __fdiv_rn((float)t6, 6.0f);
-        o[5] = __fdiv_rn((float)t5, 5.0f);
-    }
-}
-
-struct EdgeState {
-    float sum;
-};
-
-// Phase E2: the column chain of one inexact column (lane = column), continued across bands and
-// written in terms of the OUTPUT row o (box_one_d_float, pdqhash.rs:341-396, window WC, length H):
-//   grow   o in [0, HT]          sum += in[o+HB]
-//   slide  o in [HT+1, H-HALF]   sum += in[o+HB]; sum -= in[o-HT-1]
-//   shrink o in [H-HALF+1, H-1]  sum -= in[o-HT-1]
-// Only the two dependent adds per row are sequential.  Rows go four at a time: the entering
-// values (sE[slot(row)]) and the leaving ones (an 8-row ring that survives across bands) are
-// loaded up front, so the loop runs at add latency; the running sums overwrite sE[slot(o)]
-// (slot(o) <= every input slot still unread) and are divided by the window size afterwards by
-// the whole CTA (edge_divide).
-template <int WC>
-__device__ __forceinline__ void edge_chain(EdgeState &st, float *sE, float *sRing, int lane, int H, int b0,
-                                           int rows_out, int Lr0) {
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
-    static_assert(WC >= 4, "chunks of 4 rows need the leaving rows to predate the chunk");
-    if (b0 == 0) {  // pdqhash.rs:366-370: the leading half window, no output
-        for (int i = 0; i < HALF - 1; i++) {
-            const float x = sE[(i - Lr0) * 6 + lane];
-            st.sum = __fadd_rn(st.sum, x);
-            sRing[(i & 7) * 6 + lane] = x;
-        }
-    }
-    const int oend = b0 + rows_out;
-    for (int o0 = b0; o0 < oend; o0 += 4) {
-        float x[4], old[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int o = o0 + k, rin = o + HB, rout = o - HT - 1;
-            x[k] = (o < oend && rin < H) ? sE[(rin - Lr0) * 6 + lane] : 0.0f;
-            old[k] = (o < oend && rout >= 0) ? sRing[(rout & 7) * 6 + lane] : 0.0f;
-        }
-        float res[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int o = o0 + k;
-            if (o <= H - HALF) st.sum = __fadd_rn(st.sum, x[k]);   // grow and slide take a new row in
-            if (o > HT) st.sum = __fsub_rn(st.sum, old[k]);        // slide and shrink drop the oldest
-            res[k] = st.sum;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int o = o0 + k, rin = o + HB;
-            if (o < oend) {
-                if (rin < H) sRing[(rin & 7) * 6 + lane] = x[k];
-                sE[(o - Lr0) * 6 + lane] = res[k];
-            }
-        }
-    }
-}
-
-// sum / curr_win for the band's edge-column outputs (pdqhash.rs:375, :383, :392); curr_win is the
-// number of rows of the clipped column window.  Run by the 32 lanes of the edge warp.
-template <int WC>
-__device__ __forceinline__ void edge_divide(float *sE, int H, int b0, int rows_out, int Lr0, int lane) {
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
-    for (int idx = lane; idx < rows_out * 6; idx += 32) {
-        const int o = b0 + idx / 6;
-        const int cnt = min(H - 1, o + HB) - max(0, o - HT) + 1;
-        float *p = sE + (o - Lr0) * 6 + (idx % 6);
-        *p = __fdiv_rn(*p, (float)cnt);
+        float *o = sE + lr;
+        o[0 * EDGE_PITCH] = __fdiv_rn((float)s5, 5.0f);
+        o[1 * EDGE_PITCH] = __fdiv_rn((float)s6, 6.0f);
+        o[2 * EDGE_PITCH] = __fdiv_rn((float)s7, 7.0f);
+        o[3 * EDGE_PITCH] = __fdiv_rn((float)t7, 7.0f);
+        o[4 * EDGE_PITCH] = __fdiv_rn((float)t6, 6.0f);
+        o[5 * EDGE_PITCH] = __fdiv_rn((float)t5, 5.0f);
     }
 }
 
@@ -725,44 +654,54 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
     }
 }
 
-// The six inexact columns for a whole chunk of images, one warp per image (the 8-warp variant of
-// the main kernel has no edge warp): the same edge_p1 -> edge_chain -> edge_divide pipeline over
-// blocks of EDGE_ROWS rows, results to p2e[img][row][6].  It reads the first and last 48-byte chunk
-// of every source row (~4 % of the pixels) and finishes in tens of microseconds.
-constexpr int EDGE_ROWS = 96;
+// The six inexact columns for a whole chunk of images, one CTA of EDGE_THREADS threads per image:
+// edge_p1 over all rows (one thread per row), then the column pass of box_one_d_float (pdqhash.rs:
+// 341-396) on each of the six columns -- the same in-place walk pass 4 uses, one lane per column, plus
+// the shrink phase -- then the division by the clipped window size, results to p2e[img][row][6].
+// It reads the first and last 48 bytes of every source row (~4 % of the pixels, 32-byte sectors).
+constexpr int EDGE_THREADS = 128;
 
 template <int LAYOUT, bool DOWN2, int WC>
-__global__ void __launch_bounds__(256) pdq_edge_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch,
-                                                       int64_t n, int H, float *__restrict__ p2e) {
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF;
-    __shared__ float s_e[8][(EDGE_ROWS + 7) * 6];
-    __shared__ float s_ring[8][8 * 6];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t img = (int64_t)blockIdx.x * 8 + warp;
-    if (img >= n) return;   // warps are independent: no block-wide barrier below
-    const uint8_t *src = px + (size_t)img * img_pitch;
-    float *sE = s_e[warp], *sRing = s_ring[warp];
-    EdgeState est;
-    est.sum = 0.0f;
-    for (int b0 = 0; b0 < H; b0 += EDGE_ROWS) {
-        const int rows_out = min(EDGE_ROWS, H - b0);
-        const int Lr0 = b0 - HT;
-        const int nL = rows_out + WC - 1;
-        edge_p1<LAYOUT, DOWN2>(src, row_pitch, H, Lr0, nL, sE, lane);
-        __syncwarp();
-        if (lane < 6) edge_chain<WC>(est, sE, sRing, lane, H, b0, rows_out, Lr0);
-        __syncwarp();
-        edge_divide<WC>(sE, H, b0, rows_out, Lr0, lane);
-        __syncwarp();
-        float *out = p2e + ((size_t)img * H + b0) * 6;
-        for (int idx = lane; idx < rows_out * 6; idx += 32) out[idx] = sE[HT * 6 + idx];
-        __syncwarp();
+__global__ void __launch_bounds__(EDGE_THREADS) pdq_edge_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch,
+                                                                int64_t n, int H, float *__restrict__ p2e) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+    __shared__ __align__(16) float sE[6 * EDGE_PITCH];
+    __shared__ float shr[6 * 4];   // the shrink-phase sums
+    const int t = threadIdx.x;
+    for (int64_t img = blockIdx.x; img < n; img += gridDim.x) {
+        edge_p1<LAYOUT, DOWN2, EDGE_THREADS>(px + (size_t)img * img_pitch, row_pitch, H, sE, t);
+        __syncthreads();
+        if (t < 6) {
+            float *col = sE + t * EDGE_PITCH;
+            float leave[HB > 0 ? HB : 1];
+#pragma unroll
+            for (int k = 0; k < HB; k++) leave[k] = col[H - WC + k];   // the walk overwrites them
+            float sum = 0.0f, prev[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) prev[k] = 0.0f;
+            p4_walk<WC>(col, 0, H, sum, prev);   // col[i] = window sum after row i has entered
+            sum = col[H - 1];
+#pragma unroll
+            for (int k = 0; k < HB; k++) {
+                sum = __fsub_rn(sum, leave[k]);
+                shr[t * 4 + k] = sum;
+            }
+        }
+        __syncthreads();
+        float *out = p2e + (size_t)img * H * 6;
+        for (int idx = t; idx < H * 6; idx += EDGE_THREADS) {
+            const int o = idx / 6, c = idx - 6 * o;
+            const int cnt = min(H - 1, o + HB) - max(0, o - HT) + 1;   // pdqhash.rs:375, :383, :392
+            const float v = o >= H - HB ? shr[c * 4 + (o - (H - HB))] : sE[c * EDGE_PITCH + o + HB];
+            out[idx] = __fdiv_rn(v, (float)cnt);
+        }
+        __syncthreads();
     }
 }
 
 template <int LAYOUT, bool DOWN2, int WC>
 int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
-    pdq_edge_kernel<LAYOUT, DOWN2, WC><<<cdiv((size_t)a.n, 8), 256, 0, ctx->stream>>>(
+    pdq_edge_kernel<LAYOUT, DOWN2, WC><<<(unsigned)(a.n < 16 * 148 * 4 ? a.n : 16 * 148 * 4), EDGE_THREADS, 0, ctx->stream>>>(
         a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
     RH_LAUNCHED(ctx, "pdq_edge_kernel");
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
