@@ -260,3 +260,30 @@ def test_scanner_style_batching_feeder(ctx, orc):
         assert np.array_equal(res[k]["hash"], orc.to_hash(coeffs))
         assert np.array_equal(res[k]["coeffs"], coeffs)
         assert res[k]["quality"] == q and res[k]["quality_100"] == orc.quality_100(q)
+
+
+@pytest.mark.parametrize("shape,pad_row,pad_img", [((768, 1024, 3), 64, 4096), ((384, 512, 3), 16, 0),
+                                                   ((384, 512, 4), 48, 256), ((100, 449, 3), 5, 33)])
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_row_and_image_pitches(ctx, orc, shape, pad_row, pad_img, device_resident):
+    """rh_pdq_hash_batch with padded rows and padded images (the caller's pitches): the fused kernel's
+    strided front end (16-byte aligned pitches), and the generic pipeline for unaligned ones."""
+    import torch
+    from rupphash_b200 import _lib
+    h, w, ch = shape
+    n = 5
+    imgs = synth_images(n, h, w, seed=h + 3 * w + pad_row, channels=ch)
+    want = orc.pdq_batch(imgs, layout={3: 0, 4: 1}[ch], threads=4, want_coeffs=True)
+    row_pitch = w * ch + pad_row
+    img_pitch = h * row_pitch + pad_img
+    buf = np.full((n * img_pitch,), 0xA5, np.uint8)      # the padding must never be read as pixels
+    for k in range(n):
+        rows = buf[k * img_pitch: k * img_pitch + h * row_pitch].reshape(h, row_pitch)
+        rows[:, : w * ch] = imgs[k].reshape(h, w * ch)
+    got = {"hash": np.zeros((n, 32), np.uint8), "quality": np.zeros(n, np.float32),
+           "coeffs": np.zeros((n, 256), np.float32), "valid": np.zeros(n, np.uint8)}
+    src = torch.from_numpy(buf).cuda() if device_resident else buf
+    ctx.check(_lib.lib().rh_pdq_hash_batch(ctx.handle, _lib.ptr(src), {3: 0, 4: 1}[ch], n, w, h, row_pitch, img_pitch,
+                                           _lib.ptr(got["hash"]), _lib.ptr(got["quality"]), _lib.ptr(got["coeffs"]),
+                                           None, _lib.ptr(got["valid"])))
+    check_exact(got, want)
