@@ -93,6 +93,30 @@ def group_with_pdqhash(hashes, similarity, coefficients=None, quality100=None, h
     return group_files_generic(hashes, similarity, has_hash=has_hash, variants=variants, low_conf=low_conf, ctx=ctx)
 
 
+def regroup_from_cache(hash_values, coeff_values, q100, similarity, ctx=None):
+    """Group a library from the reference's cache entries alone -- no pixels, no re-hashing.
+
+    hash_values / coeff_values: per file, the plaintext hash_db / coeff_db value (cachefmt.py) or None;
+    q100: per file, the TAG_DERIVED_PDQ_QUALITY short or None.  As in PdqStrategy (scanner.rs:1611-1637):
+    a file with cached coefficients queries with its 8 dihedral variants (recomputed on the device from
+    the coefficients), a file without them with its own hash; quality < 50 marks it low-confidence,
+    unknown quality counts as good (scanner.rs:1631-1636)."""
+    from . import cachefmt
+    ctx = ctx or default_context()
+    hashes, has_hash, coeffs, has_coeffs, q = cachefmt.load_cached(hash_values, coeff_values, q100)
+    n = len(hashes)
+    variants = np.zeros((n, 8, 32), np.uint8)
+    variants[:, 0] = hashes
+    n_variants = np.ones(n, np.uint8)
+    idx = np.flatnonzero(has_coeffs & has_hash)
+    if idx.size:
+        variants[idx] = pdqhash.dihedral_from_coeffs(coeffs[idx], ctx)
+        n_variants[idx] = 8
+    low_conf = np.array([is_low_confidence(v) for v in q], np.uint8)
+    return group_files_generic(hashes, similarity, has_hash=has_hash, variants=variants, n_variants=n_variants,
+                               low_conf=low_conf, ctx=ctx)
+
+
 def edges(hashes, similarity, has_hash=None, variants=None, n_variants=None, low_conf=None, cap=1 << 20, ctx=None):
     """Debug view: the (unordered) edge list of the same search -> (edges[k, 2], comparison_count)."""
     ctx = ctx or default_context()
