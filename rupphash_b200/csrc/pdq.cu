@@ -2,7 +2,8 @@
 //
 // Entry points: rh_pdq_hash_batch, rh_pdq_from_buffer64, rh_pdq_hash_from_coeffs,
 // rh_pdq_dihedral_from_coeffs.  Two device pipelines produce the 64 x 64 buffer:
-//   * the fused kernel of pdq_fused.cuh for planes 449..512 px wide (both BASELINE shapes),
+//   * the fused kernel of pdq_fused.cu for planes 512 px wide and 193..512 px high (both BASELINE
+//     shapes; 8:3 to 1:1 landscape shapes in general),
 //   * the generic pipeline below for every other supported size: one thread walks one line
 //     exactly like box_one_d_float (pdqhash.rs:341-396), planes live in device scratch.
 // Both end in pdq_tail.cuh.  Arithmetic is f32 with explicit round-to-nearest mul/add/div

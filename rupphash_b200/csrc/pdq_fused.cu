@@ -1,8 +1,8 @@
 // pdq_fused.cu -- the bandwidth kernel of hot path #1: RGB8/RGBA8/Luma8 pixels -> luma601 ->
 // (2x Box pre-downsample) -> two Jarosz box-filter repetitions -> 64x64 decimation -> quality,
-// DCT, median, hash, in ONE persistent kernel for planes 512 px wide (both BASELINE shapes:
-// 1024x768 -> 512x384 and 512x512).  Replaces pdqhash.rs:166-262 for those shapes; every other
-// shape takes the generic pipeline in pdq.cu.  Results are bit-identical to the reference's
+// DCT, median, hash, in ONE persistent kernel for planes 512 px wide and 193..512 px high (both
+// BASELINE shapes: 1024x768 -> 512x384 and 512x512; 16:9 -> 512x288 ...).  Replaces
+// pdqhash.rs:166-262 for those shapes; every other shape takes the generic pipeline in pdq.cu.  Results are bit-identical to the reference's
 // sequential float arithmetic (tools/fused_model.py proves the restructuring on the CPU).
 //
 // Why it is not four float passes.  With a row window of 8 (pdqhash.rs:246: ceil(512/64)):
@@ -715,7 +715,10 @@ int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
 
 template <int LAYOUT, bool DOWN2>
 int dispatch_wc(rh_ctx *ctx, const FusedArgs &a, int grid, int wc) {
+    if (wc == 4) return launch_fused<LAYOUT, DOWN2, 4>(ctx, a, grid);
+    if (wc == 5) return launch_fused<LAYOUT, DOWN2, 5>(ctx, a, grid);
     if (wc == 6) return launch_fused<LAYOUT, DOWN2, 6>(ctx, a, grid);
+    if (wc == 7) return launch_fused<LAYOUT, DOWN2, 7>(ctx, a, grid);
     if (wc == 8) return launch_fused<LAYOUT, DOWN2, 8>(ctx, a, grid);
     return fail(ctx, RH_EUNSUPPORTED, "fused PDQ kernel: column window not instantiated");
 }
@@ -724,11 +727,12 @@ int dispatch_wc(rh_ctx *ctx, const FusedArgs &a, int grid, int wc) {
 
 namespace rh {
 
-// planes 512 wide whose column window ceil(H / 64) is 6 or 8 (H in 321..384 or 449..512)
+// planes 512 wide whose column window ceil(H / 64) is 4 .. 8 (H in 193..512: every landscape shape from
+// 8:3 to 1:1 after the reference's resize to 512 wide)
 int pdq_fused_supported(int W, int H) {
     if (W != FW || H > 512) return 0;
     const int wc = (H + 63) / 64;
-    return wc == 6 || wc == 8;
+    return wc >= 4 && wc <= 8;
 }
 
 // 128-bit loads need 16-byte aligned rows

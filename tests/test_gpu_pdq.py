@@ -95,7 +95,11 @@ def test_hash_and_dihedral_from_coeffs(ctx, orc):
                                    (64, 64, 3), (5, 5, 3), (37, 5, 3), (300, 100, 3), (257, 511, 3), (100, 449, 3),
                                    (720, 1024, 3), (1024, 640, 4), (480, 500), (1024, 1024, 3), (341, 512),
                                    (700, 1024, 4), (900, 1024), (330, 512, 3), (449, 512, 3), (321, 512, 4),
-                                   (642, 1024, 3), (385, 512, 3)])
+                                   (642, 1024, 3), (385, 512, 3),
+                                   # column windows 4, 5, 7 of the fused kernel (16:9, 2:1, 8:7 ... shapes)
+                                   (576, 1024, 3), (288, 512, 3), (448, 512, 3), (896, 1024, 4), (400, 512),
+                                   (250, 512, 3), (193, 512, 3), (256, 512, 4), (257, 512, 3), (320, 512),
+                                   (386, 512, 3), (512, 1024, 3), (640, 1024), (192, 512, 3)])
 def test_hash_batch_bit_exact(ctx, orc, shape):
     from rupphash_b200 import pdqhash
     h, w = shape[:2]
