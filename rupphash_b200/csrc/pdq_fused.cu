@@ -2,8 +2,9 @@
 // (2x Box pre-downsample) -> two Jarosz box-filter repetitions -> 64x64 decimation -> quality,
 // DCT, median, hash, in ONE persistent kernel for planes 512 px wide and 193..512 px high (both
 // BASELINE shapes: 1024x768 -> 512x384 and 512x512; 16:9 -> 512x288 ...).  Replaces
-// pdqhash.rs:166-262 for those shapes; every other shape takes the generic pipeline in pdq.cu.  Results are bit-identical to the reference's
-// sequential float arithmetic (tools/fused_model.py proves the restructuring on the CPU).
+// pdqhash.rs:166-262 for those shapes; every other shape takes the generic pipeline in pdq.cu.
+// Results are bit-identical to the reference's sequential float arithmetic (tools/fused_model.py
+// proves the restructuring on the CPU).
 //
 // Why it is not four float passes.  With a row window of 8 (pdqhash.rs:246: ceil(512/64)):
 //   * pass 1 (rows) of u8 luma is exact -- P1 = H/8, H an integer <= 2040 -- except in the six
