@@ -85,49 +85,110 @@ __global__ void luma_plane_kernel(const uint8_t *__restrict__ px, size_t row_pit
     L[idx] = (uint8_t)v;
 }
 
-// One thread per line: box_one_d_float (pdqhash.rs:341-396) verbatim -- sequential running
-// sum, IEEE division by the current window, four phases.
-template <typename Tin>
-__global__ void box_pass_kernel(const Tin *__restrict__ in, float *__restrict__ out, int n, int lines, int len,
-                                int line_stride, int elem_stride, size_t img_stride, int win) {
-    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= (size_t)n * lines) return;
-    const size_t img = t / lines;
-    const int line = (int)(t % lines);
-    const Tin *src = in + img * img_stride + (size_t)line * line_stride;
-    float *dst = out + img * img_stride + (size_t)line * line_stride;
-    const int lim = len > 1 ? len : 1;
+// u8 plane [R][C] -> [C][R] per image (32 x 32 tiles through shared memory, both sides coalesced).
+__global__ void transpose_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int R, int C) {
+    __shared__ uint8_t tile[32][33];
+    const size_t img = blockIdx.z;
+    const uint8_t *src = in + img * (size_t)R * C;
+    uint8_t *dst = out + img * (size_t)R * C;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int r = r0 + k, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[k][threadIdx.x] = src[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int c = c0 + k, r = r0 + threadIdx.x;
+        if (r < R && c < C) dst[(size_t)c * R + r] = tile[threadIdx.x][k];
+    }
+}
+
+// One pass of the Jarosz filter: box_one_d_float (pdqhash.rs:341-396) verbatim -- sequential running
+// sum, IEEE division by the current window, four phases -- along the ROW index i of a row-major
+// [R][C] plane.  One thread per column j, so every load is coalesced across the warp.  With TOUT the
+// result is written transposed ([C][R]): a warp stages 32 x 32 outputs in shared memory and writes
+// them as 32 coalesced rows, which turns the next pass (along the other axis) into the same
+// coalesced walk.  generic_chunk chains four of them: L^T -> A -> B^T -> A -> B.
+constexpr int WALK_WARPS = 4;
+template <typename Tin, bool TOUT>
+__global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__restrict__ in, float *__restrict__ out, int n,
+                                                                 int R, int C, int win) {
+    __shared__ float tiles[WALK_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ctiles = (C + 31) / 32;
+    const size_t wid = (size_t)blockIdx.x * WALK_WARPS + warp;   // (image, column tile)
+    if (wid >= (size_t)n * ctiles) return;                       // whole warps leave: no block-wide barrier below
+    const size_t img = wid / ctiles;
+    const int j0 = (int)(wid % ctiles) * 32;
+    const int j = min(j0 + lane, C - 1);                         // lanes past the edge shadow the last column
+    const bool valid = j0 + lane < C;
+    const Tin *src = in + img * (size_t)R * C + j;
+    float *dst = out + img * (size_t)R * C;
+    float(*tile)[33] = tiles[warp];
+    const int lim = R > 1 ? R : 1;
     win = win < 1 ? 1 : (win > lim ? lim : win);
     const int half = (win + 2) / 2;
-    const int phase_1 = half - 1, phase_2 = win - half + 1, phase_3 = len > win ? len - win : 0, phase_4 = half - 1;
-    size_t li = 0, ri = 0, oi = 0;
+    const int phase_1 = half - 1, phase_2 = win - half + 1, phase_3 = R > win ? R - win : 0, phase_4 = half - 1;
+    int li = 0, ri = 0, oi = 0;
     float sum = 0.0f, curr = 0.0f;
+    // one output of row oi; TOUT: staged, flushed when the 32-row tile (or the plane) is complete
+    auto emit = [&](float v) {
+        if (!TOUT) {
+            if (valid) dst[(size_t)oi * C + j] = v;
+        } else {
+            tile[oi & 31][lane] = v;
+            if ((oi & 31) == 31 || oi == R - 1) {
+                const int o0 = oi & ~31, cnt = (oi & 31) + 1;
+                __syncwarp();
+                for (int k = 0; k < 32; k++) {
+                    const int jj = j0 + k;
+                    if (jj < C && lane < cnt) dst[(size_t)jj * R + o0 + lane] = tile[lane][k];
+                }
+                __syncwarp();
+            }
+        }
+        oi++;
+    };
     for (int i = 0; i < phase_1; i++) {
-        sum = __fadd_rn(sum, (float)src[ri]);
+        sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
         curr += 1.0f;
-        ri += elem_stride;
+        ri++;
     }
     for (int i = 0; i < phase_2; i++) {
-        sum = __fadd_rn(sum, (float)src[ri]);
+        sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
         curr += 1.0f;
-        dst[oi] = __fdiv_rn(sum, curr);
-        ri += elem_stride;
-        oi += elem_stride;
+        emit(__fdiv_rn(sum, curr));
+        ri++;
     }
-    for (int i = 0; i < phase_3; i++) {
-        sum = __fadd_rn(sum, (float)src[ri]);
-        sum = __fsub_rn(sum, (float)src[li]);
-        dst[oi] = __fdiv_rn(sum, curr);
-        li += elem_stride;
-        ri += elem_stride;
-        oi += elem_stride;
+    int i3 = 0;
+    for (; i3 + 8 <= phase_3; i3 += 8) {   // eight steps with their sixteen loads issued up front
+        float xin[8], xout[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            xin[k] = (float)src[(size_t)(ri + k) * C];
+            xout[k] = (float)src[(size_t)(li + k) * C];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            sum = __fadd_rn(sum, xin[k]);
+            sum = __fsub_rn(sum, xout[k]);
+            emit(__fdiv_rn(sum, curr));
+        }
+        li += 8;
+        ri += 8;
+    }
+    for (; i3 < phase_3; i3++) {
+        sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
+        sum = __fsub_rn(sum, (float)src[(size_t)li * C]);
+        emit(__fdiv_rn(sum, curr));
+        li++;
+        ri++;
     }
     for (int i = 0; i < phase_4; i++) {
-        sum = __fsub_rn(sum, (float)src[li]);
+        sum = __fsub_rn(sum, (float)src[(size_t)li * C]);
         curr -= 1.0f;
-        dst[oi] = __fdiv_rn(sum, curr);
-        li += elem_stride;
-        oi += elem_stride;
+        emit(__fdiv_rn(sum, curr));
+        li++;
     }
 }
 
@@ -325,15 +386,22 @@ int generic_chunk(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int 
     else
         RH_TRY(launch_luma<RH_LAYOUT_LUMA8>(ctx, down2, d_px, row_pitch, img_pitch, n, W, H, L));
     const int w_rows = (W + 63) / 64, w_cols = (H + 63) / 64;  // pdqhash.rs:246-247
-    // rep 1 (pdqhash.rs:422-425): rows L -> A, cols A -> B; rep 2: rows B -> A, cols A -> B
-    box_pass_kernel<uint8_t><<<cdiv((size_t)n * H, 128), 128, 0, st>>>(L, A, n, H, W, W, 1, plane, w_rows);
-    RH_LAUNCHED(ctx, "box_pass_kernel");
-    box_pass_kernel<float><<<cdiv((size_t)n * W, 128), 128, 0, st>>>(A, B, n, W, H, 1, W, plane, w_cols);
-    RH_LAUNCHED(ctx, "box_pass_kernel");
-    box_pass_kernel<float><<<cdiv((size_t)n * H, 128), 128, 0, st>>>(B, A, n, H, W, W, 1, plane, w_rows);
-    RH_LAUNCHED(ctx, "box_pass_kernel");
-    box_pass_kernel<float><<<cdiv((size_t)n * W, 128), 128, 0, st>>>(A, B, n, W, H, 1, W, plane, w_cols);
-    RH_LAUNCHED(ctx, "box_pass_kernel");
+    // rep 1 (pdqhash.rs:422-425): rows L -> A, cols A -> B; rep 2: rows B -> A, cols A -> B.  Every pass
+    // is the coalesced walk along the row index, so the row passes run on transposed planes:
+    //   L [H][W] -> L^T [W][H] -(rows, win w_rows)-> A [H][W] -(cols, w_cols)-> B^T [W][H] -(rows)-> A -(cols)-> B
+    RH_TRY(scratch(ctx, S_W9, plane * n, &p));
+    uint8_t *LT = (uint8_t *)p;
+    transpose_u8_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), n), dim3(32, 8), 0, st>>>(L, LT, H, W);
+    RH_LAUNCHED(ctx, "transpose_u8_kernel");
+    const unsigned g_rows = cdiv((size_t)n * cdiv(H, 32), WALK_WARPS), g_cols = cdiv((size_t)n * cdiv(W, 32), WALK_WARPS);
+    box_walk_kernel<uint8_t, true><<<g_rows, 32 * WALK_WARPS, 0, st>>>(LT, A, n, W, H, w_rows);
+    RH_LAUNCHED(ctx, "box_walk_kernel");
+    box_walk_kernel<float, true><<<g_cols, 32 * WALK_WARPS, 0, st>>>(A, B, n, H, W, w_cols);
+    RH_LAUNCHED(ctx, "box_walk_kernel");
+    box_walk_kernel<float, true><<<g_rows, 32 * WALK_WARPS, 0, st>>>(B, A, n, W, H, w_rows);
+    RH_LAUNCHED(ctx, "box_walk_kernel");
+    box_walk_kernel<float, false><<<g_cols, 32 * WALK_WARPS, 0, st>>>(A, B, n, H, W, w_cols);
+    RH_LAUNCHED(ctx, "box_walk_kernel");
     pdq_tail_kernel<SRC_PLANE><<<n, TAIL_THREADS, 0, st>>>(B, W, H, d_dct, out, out_offset);
     RH_LAUNCHED(ctx, "pdq_tail_kernel");
     return RH_OK;
