@@ -57,7 +57,8 @@ def test_restructured_algorithm_is_bit_exact(orc):
     import fused_model
     from rupphash_b200.synth import synth_images
     rng = np.random.default_rng(1)
-    for (h, w) in [(384, 512), (341, 512), (512, 512)]:
+    # column windows 6, 6, 8 (the BASELINE shapes) and 4, 5, 7 (the other heights the fused kernel accepts)
+    for (h, w) in [(384, 512), (341, 512), (512, 512), (193, 512), (288, 512), (448, 512)]:
         for luma in (orc.luma601(synth_images(1, h, w, seed=h)[0]).reshape(h, w),
                      rng.integers(0, 256, size=(h, w), dtype=np.uint8)):
             _, _, ref = orc.pdq_from_luma(luma)
