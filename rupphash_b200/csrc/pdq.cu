@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pdq_luma.cuh"
 #include "pdq_tail.cuh"
 
 namespace rh {
@@ -85,21 +86,60 @@ __global__ void luma_plane_kernel(const uint8_t *__restrict__ px, size_t row_pit
     L[idx] = (uint8_t)v;
 }
 
-// u8 plane [R][C] -> [C][R] per image (32 x 32 tiles through shared memory, both sides coalesced).
-__global__ void transpose_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int R, int C) {
-    __shared__ uint8_t tile[32][33];
+// The same front end, eight plane pixels per thread from 128-bit loads (pdq_luma.cuh: the fused kernel's
+// DP2A / FMA luma): for 16-byte aligned rows and plane widths that are multiples of 8.
+template <int LAYOUT, bool DOWN2>
+__global__ void luma_plane8_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch, int n, int W,
+                                   int H, uint8_t *__restrict__ L) {
+    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+    constexpr int SPP = DOWN2 ? 2 : 1;
+    constexpr int BYTES = 8 * SPP * CH;
+    constexpr int NW = BYTES / 4;
+    const int w8 = W / 8;
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t per = (size_t)w8 * H;
+    if (idx >= per * n) return;
+    const size_t img = idx / per;
+    const int y = (int)((idx % per) / w8), x8 = (int)(idx % w8);
+    const uint8_t *p = px + img * img_pitch + (size_t)(y * SPP) * row_pitch + (size_t)x8 * BYTES;
+    uint32_t w0[NW], w1[DOWN2 ? NW : 1];
+    load_chunk<BYTES>(p, w0);
+    if (DOWN2) load_chunk<BYTES>(p + row_pitch, w1);
+    *reinterpret_cast<uint2 *>(L + img * (size_t)W * H + (size_t)y * W + 8 * x8) = luma8<LAYOUT, DOWN2, NW>(w0, w1);
+}
+
+// u8 plane [R][C] -> [C][R] per image: 64 x 64 tiles through shared memory, 32-bit accesses on both
+// sides when R and C are multiples of 4 (byte accesses otherwise).
+__global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int R, int C) {
+    __shared__ uint8_t tile[64][64 + 4];
     const size_t img = blockIdx.z;
     const uint8_t *src = in + img * (size_t)R * C;
     uint8_t *dst = out + img * (size_t)R * C;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int r = r0 + k, c = c0 + threadIdx.x;
-        if (r < R && c < C) tile[k][threadIdx.x] = src[(size_t)r * C + c];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 bytes each per step
+    const bool vec = ((R | C) & 3) == 0;
+    for (int k = ty; k < 64; k += 16) {
+        const int r = r0 + k, c = c0 + 4 * tx;
+        if (r >= R) continue;
+        if (vec && c + 3 < C) {
+            *reinterpret_cast<uint32_t *>(&tile[k][4 * tx]) = *reinterpret_cast<const uint32_t *>(src + (size_t)r * C + c);
+        } else {
+            for (int q = 0; q < 4; q++)
+                if (c + q < C) tile[k][4 * tx + q] = src[(size_t)r * C + c + q];
+        }
     }
     __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int c = c0 + k, r = r0 + threadIdx.x;
-        if (r < R && c < C) dst[(size_t)c * R + r] = tile[threadIdx.x][k];
+    for (int k = ty; k < 64; k += 16) {
+        const int c = c0 + k, r = r0 + 4 * tx;   // output row c, output columns r .. r + 3
+        if (c >= C) continue;
+        if (vec && r + 3 < R) {
+            const uint32_t v = (uint32_t)tile[4 * tx][k] | ((uint32_t)tile[4 * tx + 1][k] << 8) |
+                               ((uint32_t)tile[4 * tx + 2][k] << 16) | ((uint32_t)tile[4 * tx + 3][k] << 24);
+            *reinterpret_cast<uint32_t *>(dst + (size_t)c * R + r) = v;
+        } else {
+            for (int q = 0; q < 4; q++)
+                if (r + q < R) dst[(size_t)c * R + r + q] = tile[4 * tx + q][k];
+        }
     }
 }
 
@@ -161,21 +201,38 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__
         ri++;
     }
     int i3 = 0;
-    for (; i3 + 8 <= phase_3; i3 += 8) {   // eight steps with their sixteen loads issued up front
-        float xin[8], xout[8];
+    if (phase_3 >= 8) {   // eight steps at a time, the sixteen loads of the NEXT eight already in flight
+        float xin[8], xout[8], nin[8], nout[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             xin[k] = (float)src[(size_t)(ri + k) * C];
             xout[k] = (float)src[(size_t)(li + k) * C];
         }
+        for (; i3 + 8 <= phase_3; i3 += 8) {
+            const bool more = i3 + 16 <= phase_3;
+            if (more) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            sum = __fadd_rn(sum, xin[k]);
-            sum = __fsub_rn(sum, xout[k]);
-            emit(__fdiv_rn(sum, curr));
+                for (int k = 0; k < 8; k++) {
+                    nin[k] = (float)src[(size_t)(ri + 8 + k) * C];
+                    nout[k] = (float)src[(size_t)(li + 8 + k) * C];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                sum = __fadd_rn(sum, xin[k]);
+                sum = __fsub_rn(sum, xout[k]);
+                emit(__fdiv_rn(sum, curr));
+            }
+            li += 8;
+            ri += 8;
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    xin[k] = nin[k];
+                    xout[k] = nout[k];
+                }
+            }
         }
-        li += 8;
-        ri += 8;
     }
     for (; i3 < phase_3; i3++) {
         sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
@@ -359,6 +416,14 @@ template <int LAYOUT>
 int launch_luma(rh_ctx *ctx, bool down2, const uint8_t *px, size_t row_pitch, size_t img_pitch, int n, int W, int H,
                 uint8_t *L) {
     const size_t total = (size_t)n * W * H;
+    if ((W & 7) == 0 && ((reinterpret_cast<uintptr_t>(px) | row_pitch | img_pitch) & 15) == 0) {
+        if (down2)
+            luma_plane8_kernel<LAYOUT, true><<<cdiv(total / 8, 256), 256, 0, ctx->stream>>>(px, row_pitch, img_pitch, n, W, H, L);
+        else
+            luma_plane8_kernel<LAYOUT, false><<<cdiv(total / 8, 256), 256, 0, ctx->stream>>>(px, row_pitch, img_pitch, n, W, H, L);
+        RH_LAUNCHED(ctx, "luma_plane8_kernel");
+        return RH_OK;
+    }
     if (down2)
         luma_plane_kernel<LAYOUT, true><<<cdiv(total, 256), 256, 0, ctx->stream>>>(px, row_pitch, img_pitch, n, W, H, L);
     else
@@ -391,7 +456,7 @@ int generic_chunk(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int 
     //   L [H][W] -> L^T [W][H] -(rows, win w_rows)-> A [H][W] -(cols, w_cols)-> B^T [W][H] -(rows)-> A -(cols)-> B
     RH_TRY(scratch(ctx, S_W9, plane * n, &p));
     uint8_t *LT = (uint8_t *)p;
-    transpose_u8_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), n), dim3(32, 8), 0, st>>>(L, LT, H, W);
+    transpose_u8_kernel<<<dim3(cdiv(W, 64), cdiv(H, 64), n), 256, 0, st>>>(L, LT, H, W);
     RH_LAUNCHED(ctx, "transpose_u8_kernel");
     const unsigned g_rows = cdiv((size_t)n * cdiv(H, 32), WALK_WARPS), g_cols = cdiv((size_t)n * cdiv(W, 32), WALK_WARPS);
     box_walk_kernel<uint8_t, true><<<g_rows, 32 * WALK_WARPS, 0, st>>>(LT, A, n, W, H, w_rows);
@@ -486,7 +551,9 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
     // (device-resident input to the fused kernel needs 9 KB of scratch per image: one launch for up
     // to 16384 images, so that the persistent CTAs see a long queue)
-    int64_t chunk = fused ? (on_device ? 16384 : 2048) : 256;
+    // (the generic pipeline keeps ~10 B of scratch per plane pixel; 1024 images give its one-warp-per-32-columns
+    // walks enough warps to hide their load latency)
+    int64_t chunk = fused ? (on_device ? 16384 : 2048) : 1024;
     if (resize) {   // full-resolution luma + the horizontally resized plane live in scratch
         int64_t c3 = (int64_t)((size_t(1) << 30) / ((size_t)w * h + (size_t)W * h + (size_t)W * H));
         if (c3 < 1) c3 = 1;
