@@ -40,6 +40,40 @@ int main() {
     if (f->first.generate_dihedral_hashes(ctx)[0] != g->first) return 8;
     if (scanner::quality_100(0.495f) != 50 || scanner::quality_100(1.0f) != 100) return 9;
     if (phash::generate_dihedral_hashes(0x0123456789ABCDEFull)[0] != 0x0123456789ABCDEFull) return 10;
+    // batched hashing: the batch of one above is element 1 of a batch of three, bit for bit
+    std::vector<uint8_t> batch(3 * img.size());
+    for (size_t k = 0; k < 3; k++)
+        for (size_t i = 0; i < img.size(); i++) batch[k * img.size() + i] = k == 1 ? img[i] : (uint8_t)(img[i] ^ (uint8_t)(17 * k + 3));
+    auto b = pdqhash::hash_batch(ctx, batch.data(), RH_LAYOUT_RGB8, 3, 512, 384, true, true);
+    if (!b.valid[0] || !b.valid[1] || !b.valid[2]) return 11;
+    if (b.hashes[1] != g->first || b.quality[1] != g->second || b.coefficients[1] != f->first.coefficients) return 12;
+    if (b.dihedral[1] != f->first.generate_dihedral_hashes(ctx)) return 13;
+    // sharded grouping: two ranks' forests merge into the single-GPU result
+    std::vector<pdqhash::Hash> many(3000);
+    uint32_t lcg = 12345;
+    for (size_t i = 0; i < many.size(); i++)
+        for (auto &byte : many[i]) byte = (uint8_t)((lcg = lcg * 1664525u + 1013904223u) >> 24);
+    for (size_t i = 0; i < 300; i++) {   // planted near-duplicates: copy + 3 flipped bits
+        many[2000 + i] = many[i];
+        many[2000 + i][i % 32] ^= 0x15;
+    }
+    auto single = scanner::group_files_generic(ctx, many, 31);
+    auto s0 = scanner::group_files_shard(ctx, many, 31, 0, 2), s1 = scanner::group_files_shard(ctx, many, 31, 1, 2);
+    std::vector<uint32_t> forests(s0.first);
+    forests.insert(forests.end(), s1.first.begin(), s1.first.end());
+    auto merged = scanner::merge_forests(ctx, forests, 2, s0.second + s1.second);
+    if (single.groups.size() != 300 || merged.groups != single.groups || merged.comparison_count != single.comparison_count) return 14;
+    // max_dist of a group against its pivot's variants (scanner.rs:2217-2241)
+    std::vector<std::array<pdqhash::Hash, 8>> pivots(1);
+    for (auto &v : pivots[0]) v = many[0];
+    auto md = scanner::group_max_dist(ctx, pivots, {many[0], many[2000]}, {0, 0});
+    if (md.size() != 1 || md[0] != 3) return 15;
+    // 64-bit pHash path: distances, grouping, the image hash of a flat image (all AC terms 0)
+    if (hamminghash::hamming_distance(ctx, 0xFFull, 0x0Full) != 4) return 16;
+    auto g64 = scanner::group_files_generic_u64(ctx, {0x0ull, 0x7ull, 0xFFFFFFFFFFFFFFFFull}, 3);
+    if (g64.groups.size() != 1 || g64.groups[0] != std::vector<uint32_t>{0, 1}) return 17;
+    (void)phash::DctPhash::hash_image(ctx, ImageView{img.data(), 512, 384, RH_LAYOUT_RGB8});
+    if (scanner::is_low_confidence(std::nullopt) || !scanner::is_low_confidence(49) || scanner::is_low_confidence(50)) return 18;
     std::puts("harness ok");
     return 0;
 }

@@ -86,6 +86,30 @@ inline std::optional<std::pair<Hash, float>> generate_pdq(const Context &c, cons
     return std::make_pair(h, q);
 }
 
+// The scanner's batched form (scanner.rs:1409-1412 over a batch of same-sized decoded images): n
+// interleaved images back to back in host or device memory.  valid[i] == 0 is the reference's None.
+struct BatchResult {
+    std::vector<Hash> hashes;
+    std::vector<float> quality;
+    std::vector<uint8_t> valid;
+    std::vector<std::array<float, RH_PDQ_COEFFS>> coefficients;   // empty unless want_coeffs
+    std::vector<std::array<Hash, 8>> dihedral;                    // empty unless want_dihedral
+};
+inline BatchResult hash_batch(const Context &c, const uint8_t *pixels, rh_layout layout, int64_t n, int width, int height,
+                              bool want_coeffs = false, bool want_dihedral = false) {
+    BatchResult r;
+    r.hashes.resize((size_t)n);
+    r.quality.resize((size_t)n);
+    r.valid.resize((size_t)n);
+    if (want_coeffs) r.coefficients.resize((size_t)n);
+    if (want_dihedral) r.dihedral.resize((size_t)n);
+    if (n == 0) return r;
+    c.check(rh_pdq_hash_batch(c.get(), pixels, layout, n, width, height, 0, 0, r.hashes[0].data(), r.quality.data(),
+                              want_coeffs ? r.coefficients[0].data() : nullptr,
+                              want_dihedral ? r.dihedral[0][0].data() : nullptr, r.valid.data()));
+    return r;
+}
+
 }  // namespace pdqhash
 
 namespace phash {
@@ -100,6 +124,15 @@ inline std::vector<uint64_t> generate_dihedral_hashes(uint64_t h) {
     return v;
 }
 inline uint64_t calculate_rotation_invariant_hash(uint64_t h) { return rh_phash_rotation_invariant(h); }
+// DctPhash::hash_image (phash.rs:48-83): 32x32 Triangle resize, Rec.709 luma, 32x32 DCT, median of the
+// low 8x8 block -> 64 bits.  Images narrower or lower than 1 px are rejected by the library.
+struct DctPhash {
+    static uint64_t hash_image(const Context &c, const ImageView &img) {
+        uint64_t h = 0;
+        c.check(rh_phash_batch(c.get(), img.pixels, img.layout, 1, img.width, img.height, 0, 0, &h, nullptr));
+        return h;
+    }
+};
 }  // namespace phash
 
 namespace hamminghash {
@@ -111,6 +144,13 @@ constexpr uint32_t MAX_SIMILARITY_256 = RH_MAX_SIMILARITY_256;  // hamminghash.r
 inline uint32_t hamming_distance(const Context &c, const pdqhash::Hash &a, const pdqhash::Hash &b) {
     uint32_t d = 0;
     c.check(rh_hamming_distances(c.get(), a.data(), b.data(), 1, &d));
+    return d;
+}
+
+// hamminghash.rs:34-36 (batch of 1)
+inline uint32_t hamming_distance(const Context &c, uint64_t a, uint64_t b) {
+    uint32_t d = 0;
+    c.check(rh_hamming_distances_u64(c.get(), &a, &b, 1, &d));
     return d;
 }
 
@@ -147,24 +187,16 @@ inline uint16_t quality_100(float q) {
     return (uint16_t)v;
 }
 
+// scanner.rs:1588-1594, :1631-1636: unknown quality counts as good
+inline bool is_low_confidence(std::optional<uint16_t> quality100) { return quality100 && *quality100 < 50; }
+
 struct GroupResult {
     std::vector<std::vector<uint32_t>> groups;  // members ascending, groups ordered by first member
     uint64_t comparison_count;                  // scanner.rs:1778
 };
 
-// scanner.rs:1640-1817.  variants: n x 8 hashes or empty (= every file queries with its own hash);
-// low_conf / has_hash: n flags or empty.  similarity > 63 throws (the reference asserts, :1650-1655).
-inline GroupResult group_files_generic(const Context &c, const std::vector<pdqhash::Hash> &hashes, uint32_t similarity,
-                                       const std::vector<uint8_t> &has_hash = {},
-                                       const std::vector<std::array<pdqhash::Hash, 8>> &variants = {},
-                                       const std::vector<uint8_t> &low_conf = {}) {
-    const size_t n = hashes.size();
-    std::vector<uint32_t> label(n ? n : 1);
-    uint64_t count = 0;
-    c.check(rh_hamming_group(c.get(), n ? hashes[0].data() : nullptr, has_hash.empty() ? nullptr : has_hash.data(),
-                             variants.empty() ? nullptr : variants[0][0].data(), nullptr,
-                             low_conf.empty() ? nullptr : low_conf.data(), (int64_t)n, similarity, label.data(), &count));
-    // groups_map (scanner.rs:1809-1817) in canonical form
+namespace detail {
+inline GroupResult groups_from_labels(const std::vector<uint32_t> &label, size_t n, uint64_t count) {
     std::vector<uint32_t> size(n, 0), slot(n, UINT32_MAX);
     for (size_t i = 0; i < n; i++) size[label[i]]++;
     GroupResult r;
@@ -179,6 +211,73 @@ inline GroupResult group_files_generic(const Context &c, const std::vector<pdqha
         r.groups[slot[root]].push_back((uint32_t)i);
     }
     return r;
+}
+}  // namespace detail
+using detail::groups_from_labels;
+
+// scanner.rs:1640-1817.  variants: n x 8 hashes or empty (= every file queries with its own hash);
+// low_conf / has_hash: n flags or empty.  similarity > 63 throws (the reference asserts, :1650-1655).
+inline GroupResult group_files_generic(const Context &c, const std::vector<pdqhash::Hash> &hashes, uint32_t similarity,
+                                       const std::vector<uint8_t> &has_hash = {},
+                                       const std::vector<std::array<pdqhash::Hash, 8>> &variants = {},
+                                       const std::vector<uint8_t> &low_conf = {}) {
+    const size_t n = hashes.size();
+    std::vector<uint32_t> label(n ? n : 1);
+    uint64_t count = 0;
+    c.check(rh_hamming_group(c.get(), n ? hashes[0].data() : nullptr, has_hash.empty() ? nullptr : has_hash.data(),
+                             variants.empty() ? nullptr : variants[0][0].data(), nullptr,
+                             low_conf.empty() ? nullptr : low_conf.data(), (int64_t)n, similarity, label.data(), &count));
+    return groups_from_labels(label, n, count);   // groups_map (scanner.rs:1809-1817) in canonical form
+}
+
+
+// group_files_generic::<u64> with PHashStrategy (scanner.rs:1529-1577); similarity <= 15 is what the
+// reference's MIH serves (hamminghash.rs:5), the exact search accepts up to 63.
+inline GroupResult group_files_generic_u64(const Context &c, const std::vector<uint64_t> &hashes, uint32_t similarity,
+                                           const std::vector<uint8_t> &has_hash = {},
+                                           const std::vector<std::array<uint64_t, 8>> &variants = {}) {
+    const size_t n = hashes.size();
+    std::vector<uint32_t> label(n ? n : 1);
+    uint64_t count = 0;
+    c.check(rh_hamming_group_u64(c.get(), n ? hashes.data() : nullptr, has_hash.empty() ? nullptr : has_hash.data(),
+                                 variants.empty() ? nullptr : variants[0].data(), nullptr, nullptr, (int64_t)n, similarity,
+                                 label.data(), &count));
+    return detail::groups_from_labels(label, n, count);
+}
+
+// One rank's share of group_files_generic (tiles t with t % world == rank): its union-find forest and
+// edge count.  The forests of all ranks go to merge_forests; the edge counts add up.
+inline std::pair<std::vector<uint32_t>, uint64_t> group_files_shard(const Context &c, const std::vector<pdqhash::Hash> &hashes,
+                                                                    uint32_t similarity, int rank, int world,
+                                                                    const std::vector<uint8_t> &low_conf = {}) {
+    const size_t n = hashes.size();
+    std::vector<uint32_t> parent(n ? n : 1);
+    uint64_t count = 0;
+    c.check(rh_hamming_group_shard(c.get(), n ? hashes[0].data() : nullptr, nullptr, nullptr, nullptr,
+                                   low_conf.empty() ? nullptr : low_conf.data(), (int64_t)n, similarity, rank, world,
+                                   parent.data(), &count));
+    parent.resize(n);
+    return {std::move(parent), count};
+}
+// forests: world x n, rank-major (what an all-gather of the shard forests produces)
+inline GroupResult merge_forests(const Context &c, const std::vector<uint32_t> &forests, int world, uint64_t edge_count) {
+    const size_t n = world ? forests.size() / (size_t)world : 0;
+    std::vector<uint32_t> label(n ? n : 1);
+    c.check(rh_uf_merge(c.get(), forests.data(), world, (int64_t)n, label.data()));
+    return detail::groups_from_labels(label, n, edge_count);
+}
+
+// max_dist of analyze_group_with_features (scanner.rs:2217-2241) for many groups at once: per group, the
+// maximum over its members of the minimum distance to the pivot's dihedral variants.
+inline std::vector<uint32_t> group_max_dist(const Context &c, const std::vector<std::array<pdqhash::Hash, 8>> &pivot_variants,
+                                            const std::vector<pdqhash::Hash> &member_hashes,
+                                            const std::vector<uint32_t> &member_group) {
+    std::vector<uint32_t> out(pivot_variants.size());
+    if (pivot_variants.empty()) return out;
+    c.check(rh_group_max_dist(c.get(), pivot_variants[0][0].data(), nullptr,
+                              member_hashes.empty() ? nullptr : member_hashes[0].data(), member_group.data(),
+                              (int64_t)member_hashes.size(), (int64_t)pivot_variants.size(), out.data()));
+    return out;
 }
 
 }  // namespace scanner
