@@ -151,8 +151,11 @@ def run_reference(args, emit):
     from rupphash_b200.synth import synth_images
     oracle.build()
     cores = os.cpu_count() or 1
-    per_step = max(cores * 4, 64)
-    imgs = synth_images(per_step, IMG_H, IMG_W, seed=0xB200)
+    # a bounded sample per step: 16 images per host thread, so that thread start-up does not weigh on
+    # the rate (64 distinct synthetic images, cycled)
+    per_step = max(cores * 16, 128)
+    pool = synth_images(64, IMG_H, IMG_W, seed=0xB200)
+    imgs = np.ascontiguousarray(pool[np.arange(per_step) % len(pool)])
     for _ in range(args.warmup):
         oracle.pdq_batch(imgs[: max(cores, 8)], threads=cores)
     t0 = time.perf_counter()
