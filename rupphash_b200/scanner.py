@@ -263,43 +263,103 @@ def group_max_dist(groups, hashes, pivots, coefficients=None, has_hash=None, ctx
     return out
 
 
-def hash_files_batched(images_iter, batch_size=256, want_coeffs=True, ctx=None, progress=None):
+def hash_files_batched(images_iter, batch_size=256, want_coeffs=True, ctx=None, progress=None, depth=2, hasher=None,
+                       pinned=None):
     """Scanner-style feeder (scanner.rs:1202-1521 restructured): decoded images of mixed sizes
     arrive one by one (the decode stays on the host, as in the reference); same-sized images
     are collected into batches of `batch_size`, hashed on the device, and handed back in arrival
     order as dicts(hash, quality, quality_100, coeffs) -- or None where the reference returns
-    None (scanner.rs:1481-1487 keeps the file without a hash)."""
-    ctx = ctx or default_context()
+    None (scanner.rs:1481-1487 keeps the file without a hash).
+
+    The reference overlaps decode and hashing with a rayon pool feeding a DbUpdate channel
+    (scanner.rs:1202-1211, :1495-1518); here the caller's iterator (the decode) runs on the calling
+    thread while ONE submitter thread owns the rh_ctx and hashes full batches, `depth` batches may be
+    queued between them, and batches are staged in recycled page-locked buffers so that the library's
+    H2D copies run at the pinned rate.  Progress ticks (scanner.rs:1206-1211) fire per finished batch as
+    progress(done, seen).  `hasher(batch_array) -> hash_batch-style dict` replaces the device (tests);
+    `pinned` defaults to True with the device hasher."""
+    import queue
+    import threading
+    from ._lib import pinned_empty, pinned_free
+    if hasher is None:
+        ctx = ctx or default_context()
+        hasher = lambda arr: pdqhash.hash_batch(arr, want_coeffs=want_coeffs, ctx=ctx)   # noqa: E731
+        pinned = True if pinned is None else pinned
+    pinned = bool(pinned)
     results = {}
-    pending = {}
-    total = 0
+    seen = [0]
+    lock = threading.Lock()
+    work = queue.Queue(maxsize=max(1, depth))
+    free_bufs = {}            # nbytes -> [arrays]: recycled staging buffers
+    failure = []
 
-    def flush(key):
-        idxs, imgs = pending.pop(key)
-        out = pdqhash.hash_batch(np.stack(imgs), want_coeffs=want_coeffs, ctx=ctx)
-        for k, i in enumerate(idxs):
-            if not out["valid"][k]:
-                results[i] = None
+    def take_buffer(shape):
+        nbytes = int(np.prod(shape))
+        with lock:
+            pool = free_bufs.get(nbytes)
+            if pool:
+                return pool.pop().reshape(shape)
+        return pinned_empty(shape, np.uint8) if pinned else np.empty(shape, np.uint8)
+
+    def submitter():
+        while True:
+            item = work.get()
+            if item is None:
+                return
+            idxs, buf = item
+            if failure:
+                continue      # drain the queue after an error so that the producer never blocks
+            try:
+                out = hasher(buf[: len(idxs)])
+                valid, quality, hashes = np.asarray(out["valid"]), np.asarray(out["quality"]), np.asarray(out["hash"])
+                coeffs = None if out.get("coeffs") is None else np.asarray(out["coeffs"])
+                with lock:
+                    for k, i in enumerate(idxs):
+                        if not valid[k]:
+                            results[i] = None
+                            continue
+                        q = float(quality[k])
+                        results[i] = {"hash": hashes[k].copy(), "quality": q, "quality_100": quality_100(q),
+                                      "coeffs": coeffs[k].copy() if coeffs is not None else None}
+                    free_bufs.setdefault(buf.size, []).append(buf.reshape(-1))
+                    done, total = len(results), seen[0]
+                if progress:
+                    progress(done, total)
+            except BaseException as e:   # handed to the caller
+                failure.append(e)
+
+    th = threading.Thread(target=submitter, name="rh-submitter", daemon=True)
+    th.start()
+    pending = {}              # image shape -> (indices, staging buffer)
+    try:
+        for i, img in enumerate(images_iter):
+            if failure:
+                break
+            with lock:
+                seen[0] = i + 1
+            img = np.asarray(img, dtype=np.uint8)
+            h, w = img.shape[:2]
+            if w < pdqhash.MIN_HASHABLE_DIM or h < pdqhash.MIN_HASHABLE_DIM:
+                with lock:
+                    results[i] = None
                 continue
-            q = float(out["quality"][k])
-            results[i] = {"hash": out["hash"][k].copy(), "quality": q, "quality_100": quality_100(q),
-                          "coeffs": out["coeffs"][k].copy() if want_coeffs else None}
-        if progress:
-            progress(len(results), total)
-
-    for i, img in enumerate(images_iter):
-        total = i + 1
-        img = np.ascontiguousarray(img, dtype=np.uint8)
-        h, w = img.shape[:2]
-        if w < pdqhash.MIN_HASHABLE_DIM or h < pdqhash.MIN_HASHABLE_DIM:
-            results[i] = None
-            continue
-        key = img.shape
-        slot = pending.setdefault(key, ([], []))
-        slot[0].append(i)
-        slot[1].append(img)
-        if len(slot[0]) >= batch_size:
-            flush(key)
-    for key in list(pending):
-        flush(key)
-    return [results[i] for i in range(total)]
+            key = img.shape
+            slot = pending.get(key)
+            if slot is None:
+                slot = pending[key] = ([], take_buffer((batch_size,) + key))
+            slot[1][len(slot[0])] = img          # the copy into the staging buffer
+            slot[0].append(i)
+            if len(slot[0]) >= batch_size:
+                work.put(pending.pop(key))
+        for key in list(pending):
+            work.put(pending.pop(key))
+    finally:
+        work.put(None)
+        th.join()
+        if pinned:
+            for pool in free_bufs.values():
+                for b in pool:
+                    pinned_free(b)
+    if failure:
+        raise failure[0]
+    return [results[i] for i in range(seen[0])]

@@ -291,3 +291,23 @@ def test_row_and_image_pitches(ctx, orc, shape, pad_row, pad_img, device_residen
                                            _lib.ptr(got["hash"]), _lib.ptr(got["quality"]), _lib.ptr(got["coeffs"]),
                                            None, _lib.ptr(got["valid"])))
     check_exact(got, want)
+
+
+def test_feeder_pipelined_with_pinned_staging(ctx, orc):
+    """The same feeder at a realistic batch size: 70 images of two sizes through recycled page-locked
+    staging buffers and the submitter thread, against the oracle; pageable staging gives the same."""
+    from rupphash_b200 import scanner
+    a = synth_images(45, 384, 512, seed=5)
+    b = synth_images(25, 768, 1024, seed=6)
+    order = [("a", i) for i in range(45)] + [("b", i) for i in range(25)]
+    np.random.default_rng(1).shuffle(order)
+    imgs = [a[i] if t == "a" else b[i] for t, i in order]
+    res = scanner.hash_files_batched(iter(imgs), batch_size=16, ctx=ctx)
+    res2 = scanner.hash_files_batched(iter(imgs), batch_size=16, ctx=ctx, pinned=False, want_coeffs=False)
+    want_a = orc.pdq_batch(a, threads=4, want_coeffs=True)
+    want_b = orc.pdq_batch(b, threads=4, want_coeffs=True)
+    for k, (t, i) in enumerate(order):
+        w = want_a if t == "a" else want_b
+        assert np.array_equal(res[k]["hash"], w["hash"][i]) and res[k]["quality"] == w["quality"][i]
+        assert np.array_equal(res[k]["coeffs"], w["coeffs"][i])
+        assert np.array_equal(res2[k]["hash"], w["hash"][i]) and res2[k]["coeffs"] is None
