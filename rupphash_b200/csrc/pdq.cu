@@ -145,15 +145,22 @@ __global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t *__rest
 
 // One pass of the Jarosz filter: box_one_d_float (pdqhash.rs:341-396) verbatim -- sequential running
 // sum, IEEE division by the current window, four phases -- along the ROW index i of a row-major
-// [R][C] plane.  One thread per column j, so every load is coalesced across the warp.  With TOUT the
-// result is written transposed ([C][R]): a warp stages 32 x 32 outputs in shared memory and writes
-// them as 32 coalesced rows, which turns the next pass (along the other axis) into the same
-// coalesced walk.  generic_chunk chains four of them: L^T -> A -> B^T -> A -> B.
+// [R][C] plane.  One thread per column j, so every load is coalesced across the warp.  Output modes:
+//   WALK_T      the whole result, transposed ([C][R]): a warp stages 32 x 32 outputs in shared memory and
+//               writes them as 32 coalesced rows, which turns the next pass (along the other axis) into
+//               the same coalesced walk;
+//   WALK_DEC_T  only the 64 decimation samples of each line (index ((2k+1) R) / 128, pdqhash.rs:435-440),
+//               staged and written as [C][64] -- pass 4 only ever reads those columns of pass 3;
+//   WALK_DEC    only the 64 decimation samples, written as [64][C] -- the 64 x 64 buffer of the tail.
+// In the decimated modes the division is done for the kept samples only.
+// generic_chunk chains four walks: L^T -> A -> B^T -> A3 [H][64] -> B64 [64][64].
 constexpr int WALK_WARPS = 4;
-template <typename Tin, bool TOUT>
+enum { WALK_T = 0, WALK_DEC_T = 1, WALK_DEC = 2 };
+template <typename Tin, int MODE>
 __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__restrict__ in, float *__restrict__ out, int n,
                                                                  int R, int C, int win) {
-    __shared__ float tiles[WALK_WARPS][32][33];
+    constexpr int TPITCH = MODE == WALK_DEC_T ? 65 : 33;
+    __shared__ float tiles[WALK_WARPS][32 * TPITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ctiles = (C + 31) / 32;
     const size_t wid = (size_t)blockIdx.x * WALK_WARPS + warp;   // (image, column tile)
@@ -163,28 +170,37 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__
     const int j = min(j0 + lane, C - 1);                         // lanes past the edge shadow the last column
     const bool valid = j0 + lane < C;
     const Tin *src = in + img * (size_t)R * C + j;
-    float *dst = out + img * (size_t)R * C;
-    float(*tile)[33] = tiles[warp];
+    float *dst = out + img * (MODE == WALK_T ? (size_t)R * C : (size_t)64 * C);
+    float *tile = tiles[warp];
+    int next_k = 0, next_idx = R >> 7;   // decimated modes: the next sample to keep and its line index
     const int lim = R > 1 ? R : 1;
     win = win < 1 ? 1 : (win > lim ? lim : win);
     const int half = (win + 2) / 2;
     const int phase_1 = half - 1, phase_2 = win - half + 1, phase_3 = R > win ? R - win : 0, phase_4 = half - 1;
     int li = 0, ri = 0, oi = 0;
     float sum = 0.0f, curr = 0.0f;
-    // one output of row oi; TOUT: staged, flushed when the 32-row tile (or the plane) is complete
-    auto emit = [&](float v) {
-        if (!TOUT) {
-            if (valid) dst[(size_t)oi * C + j] = v;
-        } else {
-            tile[oi & 31][lane] = v;
+    // one output of row oi = sum / curr
+    auto emit = [&](float s, float c) {
+        if (MODE == WALK_T) {   // staged, flushed when the 32-row tile (or the plane) is complete
+            tile[(oi & 31) * TPITCH + lane] = __fdiv_rn(s, c);
             if ((oi & 31) == 31 || oi == R - 1) {
                 const int o0 = oi & ~31, cnt = (oi & 31) + 1;
                 __syncwarp();
                 for (int k = 0; k < 32; k++) {
                     const int jj = j0 + k;
-                    if (jj < C && lane < cnt) dst[(size_t)jj * R + o0 + lane] = tile[lane][k];
+                    if (jj < C && lane < cnt) dst[(size_t)jj * R + o0 + lane] = tile[lane * TPITCH + k];
                 }
                 __syncwarp();
+            }
+        } else if (oi == next_idx) {   // (uniform across the warp)
+            const float v = __fdiv_rn(s, c);
+            while (next_k < 64 && next_idx == oi) {   // short lines map several samples to one index
+                if (MODE == WALK_DEC_T)
+                    tile[lane * TPITCH + next_k] = v;
+                else if (valid)
+                    dst[(size_t)next_k * C + j] = v;
+                next_k++;
+                next_idx = ((2 * next_k + 1) * R) >> 7;
             }
         }
         oi++;
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__
     for (int i = 0; i < phase_2; i++) {
         sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
         curr += 1.0f;
-        emit(__fdiv_rn(sum, curr));
+        emit(sum, curr);
         ri++;
     }
     int i3 = 0;
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__
             for (int k = 0; k < 8; k++) {
                 sum = __fadd_rn(sum, xin[k]);
                 sum = __fsub_rn(sum, xout[k]);
-                emit(__fdiv_rn(sum, curr));
+                emit(sum, curr);
             }
             li += 8;
             ri += 8;
@@ -237,15 +253,23 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) box_walk_kernel(const Tin *__
     for (; i3 < phase_3; i3++) {
         sum = __fadd_rn(sum, (float)src[(size_t)ri * C]);
         sum = __fsub_rn(sum, (float)src[(size_t)li * C]);
-        emit(__fdiv_rn(sum, curr));
+        emit(sum, curr);
         li++;
         ri++;
     }
     for (int i = 0; i < phase_4; i++) {
         sum = __fsub_rn(sum, (float)src[(size_t)li * C]);
         curr -= 1.0f;
-        emit(__fdiv_rn(sum, curr));
+        emit(sum, curr);
         li++;
+    }
+    if (MODE == WALK_DEC_T) {   // the 64 samples of each of the warp's 32 lines, one 256-byte row per line
+        __syncwarp();
+        for (int l = 0; l < 32; l++) {
+            if (j0 + l >= C) break;
+            dst[(size_t)(j0 + l) * 64 + lane] = tile[l * TPITCH + lane];
+            dst[(size_t)(j0 + l) * 64 + 32 + lane] = tile[l * TPITCH + 32 + lane];
+        }
     }
 }
 
@@ -440,9 +464,11 @@ int generic_chunk(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int 
     void *p;
     RH_TRY(scratch(ctx, S_W0, plane * n, &p));
     uint8_t *L = (uint8_t *)p;
-    RH_TRY(scratch(ctx, S_W1, plane * n * sizeof(float), &p));
+    // A also takes pass 3's decimated output ([H][64]), B the final 64 x 64 buffers
+    const size_t a_floats = plane > (size_t)64 * H ? plane : (size_t)64 * H, b_floats = plane > 4096 ? plane : 4096;
+    RH_TRY(scratch(ctx, S_W1, a_floats * n * sizeof(float), &p));
     float *A = (float *)p;
-    RH_TRY(scratch(ctx, S_W2, plane * n * sizeof(float), &p));
+    RH_TRY(scratch(ctx, S_W2, b_floats * n * sizeof(float), &p));
     float *B = (float *)p;
     if (layout == RH_LAYOUT_RGB8)
         RH_TRY(launch_luma<RH_LAYOUT_RGB8>(ctx, down2, d_px, row_pitch, img_pitch, n, W, H, L));
@@ -453,21 +479,22 @@ int generic_chunk(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int 
     const int w_rows = (W + 63) / 64, w_cols = (H + 63) / 64;  // pdqhash.rs:246-247
     // rep 1 (pdqhash.rs:422-425): rows L -> A, cols A -> B; rep 2: rows B -> A, cols A -> B.  Every pass
     // is the coalesced walk along the row index, so the row passes run on transposed planes:
-    //   L [H][W] -> L^T [W][H] -(rows, win w_rows)-> A [H][W] -(cols, w_cols)-> B^T [W][H] -(rows)-> A -(cols)-> B
+    //   L [H][W] -> L^T [W][H] -(rows, win w_rows)-> A [H][W] -(cols, w_cols)-> B^T [W][H]
+    //     -(rows, the 64 decimated columns only)-> A3 [H][64] -(cols, the 64 decimated rows only)-> B64 [64][64]
     RH_TRY(scratch(ctx, S_W9, plane * n, &p));
     uint8_t *LT = (uint8_t *)p;
     transpose_u8_kernel<<<dim3(cdiv(W, 64), cdiv(H, 64), n), 256, 0, st>>>(L, LT, H, W);
     RH_LAUNCHED(ctx, "transpose_u8_kernel");
     const unsigned g_rows = cdiv((size_t)n * cdiv(H, 32), WALK_WARPS), g_cols = cdiv((size_t)n * cdiv(W, 32), WALK_WARPS);
-    box_walk_kernel<uint8_t, true><<<g_rows, 32 * WALK_WARPS, 0, st>>>(LT, A, n, W, H, w_rows);
+    box_walk_kernel<uint8_t, WALK_T><<<g_rows, 32 * WALK_WARPS, 0, st>>>(LT, A, n, W, H, w_rows);
     RH_LAUNCHED(ctx, "box_walk_kernel");
-    box_walk_kernel<float, true><<<g_cols, 32 * WALK_WARPS, 0, st>>>(A, B, n, H, W, w_cols);
+    box_walk_kernel<float, WALK_T><<<g_cols, 32 * WALK_WARPS, 0, st>>>(A, B, n, H, W, w_cols);
     RH_LAUNCHED(ctx, "box_walk_kernel");
-    box_walk_kernel<float, true><<<g_rows, 32 * WALK_WARPS, 0, st>>>(B, A, n, W, H, w_rows);
+    box_walk_kernel<float, WALK_DEC_T><<<g_rows, 32 * WALK_WARPS, 0, st>>>(B, A, n, W, H, w_rows);
     RH_LAUNCHED(ctx, "box_walk_kernel");
-    box_walk_kernel<float, false><<<g_cols, 32 * WALK_WARPS, 0, st>>>(A, B, n, H, W, w_cols);
+    box_walk_kernel<float, WALK_DEC><<<cdiv((size_t)n * 2, WALK_WARPS), 32 * WALK_WARPS, 0, st>>>(A, B, n, H, 64, w_cols);
     RH_LAUNCHED(ctx, "box_walk_kernel");
-    pdq_tail_kernel<SRC_PLANE><<<n, TAIL_THREADS, 0, st>>>(B, W, H, d_dct, out, out_offset);
+    pdq_tail_kernel<SRC_BUF64><<<n, TAIL_THREADS, 0, st>>>(B, W, H, d_dct, out, out_offset);
     RH_LAUNCHED(ctx, "pdq_tail_kernel");
     return RH_OK;
 }
