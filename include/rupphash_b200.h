@@ -36,7 +36,8 @@ typedef enum {
     RH_EINVAL = -1,       /* bad argument (incl. threshold > 63: scanner.rs:1650-1655 assert) */
     RH_ECUDA = -2,        /* CUDA runtime error */
     RH_ENOMEM = -3,       /* allocation failed */
-    RH_EUNSUPPORTED = -4  /* valid in the reference but not implemented on the device path */
+    RH_EUNSUPPORTED = -4, /* valid in the reference but not implemented on the device path */
+    RH_ENCCL = -5         /* NCCL could not be loaded / initialised, or a collective failed */
 } rh_status;
 
 /* pixel layouts accepted by the hashers (pdqhash.rs:268-284: Rgb8 / Rgba8 / Luma8) */
@@ -57,6 +58,10 @@ int rh_ctx_destroy(rh_ctx *ctx);
  * torch's current stream).  NULL restores the ctx-owned stream. */
 int rh_ctx_set_stream(rh_ctx *ctx, void *cuda_stream);
 int rh_ctx_sync(rh_ctx *ctx);
+/* Tuning knobs for benchmarks and A/B runs (never needed for correct results; the defaults are the
+ * product path): "hamming.prefilter" (-1 = chosen by the threshold, 0 / 3 / 4 = pin the kernel variant),
+ * "pdq.force_generic", "pdq.prefetch", "pdq.prefetch_rows", "pdq.phase_clocks", "pdq.variant". */
+int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value);
 const char *rh_last_error(const rh_ctx *ctx);
 const char *rh_version(void);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
@@ -208,6 +213,55 @@ int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits
 int rh_group_max_dist(rh_ctx *ctx, const uint8_t *pivot_variants, const uint8_t *n_pivot_variants,
                       const uint8_t *member_hashes, const uint32_t *member_group, int64_t n_members,
                       int64_t n_groups, uint32_t *out_max_dist);
+
+/* ------------------------------------------------------- several GPUs, one process ---- */
+
+/*
+ * rh_group: the GPUs of one box behind one handle, for a caller that is a single process (the
+ * reference calls group_with_pdqhash once from its scan thread, scanner.rs:1550-1551, :1827-1832).
+ * One rh_ctx per device, peer access between all of them, NCCL communicators from
+ * ncclCommInitAll (NCCL is loaded with dlopen here: the library has no link-time NCCL dependency).
+ *   devices   CUDA device indices, or NULL for devices 0 .. n_dev-1 (n_dev <= 0 with NULL: all)
+ *   flags     RH_GROUP_NO_NCCL: exchange with cudaMemcpyPeerAsync instead of NCCL collectives
+ *             RH_GROUP_STATIC_TILES: tile t belongs to GPU t mod n_dev (default: the GPUs claim tiles
+ *             from one counter in the first GPU's memory with NVLink atomics -- work stealing)
+ * Errors: RH_ENCCL when NCCL cannot be loaded / initialised; rh_group_last_error for the message.
+ * A group is not thread-safe (one in-flight call); rh_group_ctx gives the per-device contexts for
+ * single-device calls between group calls.
+ */
+typedef struct rh_group rh_group;
+#define RH_GROUP_NO_NCCL 1u
+#define RH_GROUP_STATIC_TILES 2u
+int rh_group_create(const int *devices, int n_dev, unsigned flags, rh_group **out);
+int rh_group_destroy(rh_group *g);
+int rh_group_size(const rh_group *g);
+rh_ctx *rh_group_ctx(rh_group *g, int i);
+const char *rh_group_last_error(const rh_group *g);
+/* NCCL version in use (0 = peer copies) and whether tiles are claimed from one pool */
+int rh_group_info(const rh_group *g, int *nccl_version, int *work_stealing);
+/* Times of the last group call in ms: [0] wall time of rh_hamming_group_multi, [1] / [2] tile kernel
+ * on the slowest / fastest GPU (CUDA events), [3] sum of the tile-kernel times over the GPUs,
+ * [4] wall time of rh_pdq_hash_batch_multi. */
+int rh_group_last_times(const rh_group *g, double *out, int n_out);
+
+/*
+ * scanner::group_files_generic (scanner.rs:1640-1817) over every GPU of the group; same arguments,
+ * same results (labels, comparison_count) as rh_hamming_group, bit-identical for any number of GPUs.
+ * Inputs: host memory (each GPU copies one slice over its own PCIe link, an NCCL all-gather over
+ * NVLink replicates them) or memory of one GPU of the group (broadcast from there).  The N x N pair
+ * matrix is tiled across the GPUs, the rank-local forests are all-gathered (n x u32 per GPU), the
+ * edge counts all-reduced, the forests merged on the first GPU.  out_label: host memory or memory
+ * of the group's first GPU.
+ */
+int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *has_hash,
+                           const uint8_t *variants, const uint8_t *n_variants, const uint8_t *low_conf,
+                           int64_t n, uint32_t similarity, uint32_t *out_label, uint64_t *out_edge_count);
+
+/* rh_pdq_hash_batch with the batch cut into one contiguous slice per GPU (host buffers; images are
+ * independent, so there is no exchange: scanner.rs:1202-1205's par_iter over files). */
+int rh_pdq_hash_batch_multi(rh_group *g, const uint8_t *pixels, int layout, int64_t n, int w, int h,
+                            size_t row_pitch, size_t img_pitch, uint8_t *out_hash, float *out_quality,
+                            float *out_coeffs, uint8_t *out_dihedral, uint8_t *out_valid);
 
 /* ------------------------------------------------------------- measurement ---- */
 

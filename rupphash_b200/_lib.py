@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("RH_B200_LIB") or os.path.join(_HERE, "librupphash_b200.so")   # RH_B200_LIB: A/B builds
 
-RH_OK, RH_EINVAL, RH_ECUDA, RH_ENOMEM, RH_EUNSUPPORTED = 0, -1, -2, -3, -4
+RH_OK, RH_EINVAL, RH_ECUDA, RH_ENOMEM, RH_EUNSUPPORTED, RH_ENCCL = 0, -1, -2, -3, -4, -5
 LAYOUT_RGB8, LAYOUT_RGBA8, LAYOUT_LUMA8 = 0, 1, 2
 MAX_SIMILARITY_64 = 15   # hamminghash.rs:5
 MAX_SIMILARITY_256 = 63  # hamminghash.rs:8
@@ -22,7 +22,7 @@ PDQ_MIN_QUALITY = 50     # scanner.rs:1579
 
 # every symbol include/rupphash_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = [
-    "rh_ctx_create", "rh_ctx_destroy", "rh_ctx_set_stream", "rh_ctx_sync", "rh_last_error", "rh_version",
+    "rh_ctx_create", "rh_ctx_destroy", "rh_ctx_set_stream", "rh_ctx_sync", "rh_ctx_set_option", "rh_last_error", "rh_version",
     "rh_kernel_launches", "rh_last_kernel_time", "rh_alloc_pinned", "rh_free_pinned",
     "rh_pdq_hash_batch", "rh_pdq_hash_from_coeffs", "rh_pdq_dihedral_from_coeffs", "rh_pdq_from_buffer64",
     "rh_phash_rotate_90", "rh_phash_rotate_180", "rh_phash_rotate_270", "rh_phash_flip_horizontal",
@@ -30,6 +30,8 @@ EXPORTS = [
     "rh_hamming_distances", "rh_hamming_distances_u64", "rh_hamming_group", "rh_hamming_group_shard",
     "rh_uf_merge", "rh_hamming_edges", "rh_hamming_group_u64", "rh_find_groups", "rh_group_max_dist",
     "rh_measure_peaks",
+    "rh_group_create", "rh_group_destroy", "rh_group_size", "rh_group_ctx", "rh_group_last_error", "rh_group_info",
+    "rh_group_last_times", "rh_hamming_group_multi", "rh_pdq_hash_batch_multi",
 ]
 
 
@@ -68,6 +70,7 @@ def _declare(L):
     L.rh_ctx_destroy.argtypes = [_vp]
     L.rh_ctx_set_stream.argtypes = [_vp, _vp]
     L.rh_ctx_sync.argtypes = [_vp]
+    L.rh_ctx_set_option.argtypes = [_vp, C.c_char_p, C.c_int]
     L.rh_last_error.argtypes = [_vp]
     L.rh_last_error.restype = C.c_char_p
     L.rh_version.restype = C.c_char_p
@@ -102,6 +105,19 @@ def _declare(L):
                                  C.POINTER(C.c_size_t)]
     L.rh_group_max_dist.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp]
     L.rh_measure_peaks.argtypes = [_vp, C.POINTER(C.c_double)]
+    L.rh_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_uint, C.POINTER(_vp)]
+    L.rh_group_destroy.argtypes = [_vp]
+    L.rh_group_size.argtypes = [_vp]
+    L.rh_group_ctx.argtypes = [_vp, C.c_int]
+    L.rh_group_ctx.restype = _vp
+    L.rh_group_last_error.argtypes = [_vp]
+    L.rh_group_last_error.restype = C.c_char_p
+    L.rh_group_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rh_group_last_times.argtypes = [_vp, C.POINTER(C.c_double), C.c_int]
+    L.rh_hamming_group_multi.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_uint32, _vp,
+                                         C.POINTER(C.c_uint64)]
+    L.rh_pdq_hash_batch_multi.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                          _vp, _vp, _vp, _vp, _vp]
 
 
 def is_torch_tensor(x) -> bool:
@@ -166,6 +182,10 @@ class Context:
     def sync(self):
         self.check(lib().rh_ctx_sync(self._h))
 
+    def set_option(self, key: str, value: int):
+        """Tuning knob for benchmarks / A-B runs (rh_ctx_set_option); defaults are the product path."""
+        self.check(lib().rh_ctx_set_option(self._h, key.encode(), int(value)))
+
     @property
     def kernel_launches(self) -> int:
         return int(lib().rh_kernel_launches(self._h))
@@ -179,6 +199,64 @@ class Context:
         out = (C.c_double * 4)()
         self.check(lib().rh_measure_peaks(self._h, out))
         return {"popc_per_s": out[0], "lop3_per_s": out[1], "h2d_gbs": out[2], "copy_gbs": out[3]}
+
+
+GROUP_NO_NCCL, GROUP_STATIC_TILES = 1, 2
+
+
+class Group:
+    """rh_group: several GPUs of one box driven from this one process (in-library NCCL / NVLink peer
+    access; no torch.distributed involved)."""
+
+    def __init__(self, devices=None, n_dev: int = 0, flags: int = 0):
+        self._h = _vp()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = lib().rh_group_create(arr, len(devices), int(flags), C.byref(self._h))
+        else:
+            rc = lib().rh_group_create(None, int(n_dev), int(flags), C.byref(self._h))
+        if rc != RH_OK:
+            self._h = _vp()
+            raise RupphashError(rc, f"rh_group_create(devices={devices}, n_dev={n_dev}) failed "
+                                    "(no usable CUDA devices, no peer access, or NCCL unavailable)")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rh_group_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def size(self) -> int:
+        return int(lib().rh_group_size(self._h))
+
+    def info(self) -> dict:
+        v, ws = C.c_int(), C.c_int()
+        lib().rh_group_info(self._h, C.byref(v), C.byref(ws))
+        return {"nccl_version": v.value, "work_stealing": bool(ws.value), "n_gpus": self.size}
+
+    def last_times(self) -> dict:
+        out = (C.c_double * 8)()
+        lib().rh_group_last_times(self._h, out, 8)
+        return {"group_wall_ms": out[0], "tile_ms_max": out[1], "tile_ms_min": out[2], "tile_ms_sum": out[3],
+                "hash_wall_ms": out[4]}
+
+    def check(self, rc: int):
+        if rc == RH_OK:
+            return
+        msg = lib().rh_group_last_error(self._h).decode("utf-8", "replace")
+        if rc == RH_EINVAL:
+            raise ValueError(f"rupphash_b200: {msg}")
+        raise RupphashError(rc, msg)
 
 
 _default_ctx: dict[int, Context] = {}

@@ -33,6 +33,15 @@ struct rh_ctx {
     void *hslot_ptr[kHostSlots] = {};
     size_t hslot_bytes[kHostSlots] = {};
     bool dct_ready = false;
+    bool timing_pending = false;   // ev_a / ev_b bracket a kernel whose time has not been read yet
+    // tuning knobs of rh_ctx_set_option (benchmarks / A-B runs); the defaults are the product path
+    int force_prefilter = -1;      // "hamming.prefilter": -1 = by threshold, 0 / 3 / 4 = pin the variant
+    int pdq_force_generic = 0;     // "pdq.force_generic"
+    int pdq_prefetch = 2;          // "pdq.prefetch": L2 prefetch mode of the fused kernel's front end
+    int pdq_prefetch_rows = 16;    // "pdq.prefetch_rows"
+    int pdq_phase_clocks = 0;      // "pdq.phase_clocks": print per-phase cycle shares after each fused launch
+    int pdq_variant = 0;           // "pdq.variant": 0 = default front end, other values = experiments
+    uint64_t stage_seq = 0;        // chunks staged so far (alternates the two H2D staging buffers across calls)
 };
 
 namespace rh {

@@ -72,9 +72,29 @@ int rh_ctx_sync(rh_ctx *ctx) {
     return RH_OK;
 }
 
+int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key) return RH_EINVAL;
+    if (!strcmp(key, "hamming.prefilter")) {
+        if (value != -1 && value != 0 && value != 3 && value != 4) return rh::fail(ctx, RH_EINVAL, "hamming.prefilter: -1, 0, 3 or 4");
+        ctx->force_prefilter = value;
+    } else if (!strcmp(key, "pdq.force_generic"))
+        ctx->pdq_force_generic = value;
+    else if (!strcmp(key, "pdq.prefetch"))
+        ctx->pdq_prefetch = value;
+    else if (!strcmp(key, "pdq.prefetch_rows"))
+        ctx->pdq_prefetch_rows = value;
+    else if (!strcmp(key, "pdq.phase_clocks"))
+        ctx->pdq_phase_clocks = value;
+    else if (!strcmp(key, "pdq.variant"))
+        ctx->pdq_variant = value;
+    else
+        return rh::fail(ctx, RH_EINVAL, "rh_ctx_set_option: unknown key");
+    return RH_OK;
+}
+
 const char *rh_last_error(const rh_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-const char *rh_version(void) { return "rupphash_b200 0.1 (sm_100a)"; }
+const char *rh_version(void) { return "rupphash_b200 0.2 (sm_100a)"; }
 
 uint64_t rh_kernel_launches(const rh_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

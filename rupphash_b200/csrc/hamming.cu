@@ -6,13 +6,21 @@
 // similarity (<= 63) the pigeonhole argument makes that set identical to the all-pairs set
 // (SURVEY.md F3), which is what the tiles below enumerate.
 //
-// Kernel shape (hamming_tiles_kernel): a CTA owns a tile of HT_TQ query rows x HT_TC candidates.
-// Candidates (8 x u32 each) sit in shared memory and are read with warp-broadcast LDS.128;
-// every thread keeps HT_RQ query rows in registers, so one candidate fetch feeds HT_RQ pairs.
+// Kernel shape (hamming_tiles_kernel): persistent CTAs claim tiles of HT_TQ query rows x HT_TC
+// candidates from a counter (in this GPU's memory, or -- multi-GPU group -- in one GPU's memory
+// reached by every GPU with NVLink atomics: the GPUs steal work from one pool, so a slower GPU
+// simply takes fewer tiles).  The candidates of a tile (8 x u32 each, 16 KB) are fetched by the
+// bulk-copy engine (cp.async.bulk + mbarrier) into one of two shared-memory stages while the
+// previous tile is being searched, and read with warp-broadcast LDS.128; every thread keeps HT_RQ
+// query rows in registers, so one candidate fetch feeds HT_RQ pairs.
 // A pair costs 8 XOR + a 4-step carry-save compression (8 LOP3) + 4 POPC instead of 8 POPC:
 // POPC issues at a quarter of the LOP3 rate, so trading POPCs for LOP3s balances the two pipes.
 // Pairs under the threshold are rare; they take a divergent slow path that applies the exact
 // edge rule (j > i, low-confidence => distance 0 only) and hooks the union-find.
+//
+// Nothing between the caller's buffers and the labels needs the host: the dense arrays, their
+// sizes, the tile count and the claim counter are produced and consumed on the device
+// (TileMeta), so a search is one stream of launches with a single synchronisation at the end.
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
@@ -21,14 +29,25 @@
 #include <new>
 
 #include "common.cuh"
+#include "hamming_internal.cuh"
+#include "tma.cuh"
 #include "unionfind.cuh"
 
 namespace {
 
 constexpr int HT_THREADS = 256;
 constexpr int HT_RQ = 4;                     // query rows per thread
-constexpr int HT_TQ = HT_THREADS * HT_RQ;    // query rows per CTA tile
-constexpr int HT_TC = 1024;                  // candidates per CTA tile (32 KB of shared memory)
+constexpr int HT_TQ = HT_THREADS * HT_RQ;    // query rows per tile
+constexpr int HT_TC = 512;                   // candidates per tile (16 KB per stage, two stages)
+constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
+
+typedef unsigned long long u64;
+
+// sizes known only on the device (files without a hash are dropped, variants per file vary)
+struct TileMeta {
+    uint32_t nc, nq;      // dense candidates / query rows
+    uint32_t n_qb, n_cb;  // query blocks of HT_TQ rows, candidate blocks of HT_TC
+};
 
 struct GroupArgs {
     const uint32_t *cand;     // [nc_pad][W] dense candidate hashes, zero padded to HT_TC rows
@@ -36,14 +55,17 @@ struct GroupArgs {
     const uint32_t *qfile;    // [nq_pad] dense file id of each query row (0xFFFFFFFF = padding)
     const uint8_t *lc;        // [nc] low-confidence flag per dense file, or nullptr
     uint32_t *parent;         // [nc] union-find forest over dense ids
-    unsigned long long *edge_count;
+    u64 *edge_count;
     uint2 *edges;             // optional edge sink (dense ids), capacity edges_cap
-    unsigned long long edges_cap;
-    unsigned long long *edges_n;
-    uint32_t nc, nq, threshold;
-    int rank, world;
-    const uint2 *tile_list;       // [n_tiles] (query block, candidate block) of every valid tile
-    uint32_t n_qb, n_tiles;
+    u64 edges_cap;
+    u64 *edges_n;
+    const TileMeta *meta;
+    const u64 *tile_start;    // [n_qb_max + 1] exclusive scan of the valid-tile count per query block
+    uint32_t n_qb_max;        // tile_start[n_qb_max] = number of valid tiles
+    u64 *next_tile;           // claim counter; claim c is tile c * claim_stride + claim_offset
+    uint32_t claim_stride, claim_offset;
+    int counter_is_remote;    // the counter may live in a peer GPU's memory (system-scope atomics)
+    uint32_t nc, threshold;   // nc is filled in from meta by the kernel
 };
 
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
@@ -79,40 +101,55 @@ __device__ __noinline__ uint32_t slow_hit(const GroupArgs *g, uint32_t d, uint32
     if (g->lc && (g->lc[qf] | g->lc[cj])) lim = 0;  // scanner.rs:1699, :1721
     if (d > lim) return 0;
     if (g->edges) {
-        unsigned long long k = atomicAdd(g->edges_n, 1ull);
+        u64 k = atomicAdd(g->edges_n, 1ull);
         if (k < g->edges_cap) g->edges[k] = make_uint2(qf, cj);
     }
+    RH_CHECK_IDX(qf, g->nc);
     rh::uf_unite(g->parent, qf, cj);
     return 1;
 }
 
 // first candidate block that can hold a pair with j > i for a query block whose smallest file id
-// is f0 (rows are ordered by file; scanner.rs:1712-1714), and the number of such blocks
+// is f0 (rows are ordered by file; scanner.rs:1712-1714)
 __device__ __forceinline__ uint32_t first_cand_block(uint32_t f0) { return (f0 + 1u) / (uint32_t)HT_TC; }
 
-// Only tiles that can contain work are launched: tile t (in the order query block major,
-// candidate block minor, valid tiles only) belongs to rank t mod world, so every rank gets the
-// same number of tiles to within one and no CTA is launched just to exit.
-__device__ __forceinline__ bool decode_tile(const GroupArgs &g, uint32_t &qb, uint32_t &cb) {
-    const uint32_t t = blockIdx.x * (uint32_t)g.world + (uint32_t)g.rank;
-    if (t >= g.n_tiles) return false;
-    const uint2 e = g.tile_list[t];
-    qb = e.x;
-    cb = e.y;
-    return true;
+// ------------------------------------------------------------ tile scheduler ----
+// Only tiles that can contain a pair with j > i exist: tile t (query block major, candidate block
+// minor) is found from the exclusive scan `tile_start`.  Warp 0 of a CTA claims the next tile with
+// one atomic, locates its query block with a 32-way search (every lane probes one point, a ballot
+// picks the interval: 3 rounds instead of 15 dependent loads for 30 000 query blocks) and starts the
+// bulk copy of its candidates.
+struct TileSched {
+    uint2 tile[2];                   // (query block, candidate block) staged in each buffer
+    __align__(8) uint64_t bar[2];    // "candidates of stage s have landed"
+};
+
+__device__ __forceinline__ uint32_t find_query_block(const u64 *tile_start, uint32_t n_qb, u64 t, int lane) {
+    uint32_t lo = 0, hi = n_qb;   // invariant: tile_start[lo] <= t, answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31u) >> 5;
+        const uint32_t p = lo + (uint32_t)lane * step;
+        const bool ok = p < hi && tile_start[p] <= t;   // monotone in the lane; lane 0 always holds
+        const uint32_t k = 31u - (uint32_t)__clz((int)__ballot_sync(0xFFFFFFFFu, ok));
+        lo += k * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
 }
 
-// (query block, candidate block) of every valid tile, in tile order: one thread per tile
-__global__ void tile_list_kernel(const uint32_t *tile_start, const uint32_t *qfile, uint32_t n_qb, uint32_t n_tiles,
-                                 uint2 *list) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint32_t lo = 0, hi = n_qb;   // largest qb with tile_start[qb] <= t
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (tile_start[mid] <= t) lo = mid; else hi = mid;
-    }
-    list[t] = make_uint2(lo, first_cand_block(qfile[(size_t)lo * HT_TQ]) + (t - tile_start[lo]));
+// warp 0, all lanes: claim a tile and describe it in sched.tile[buf]; returns its candidate block
+// (NO_TILE when the pool is empty)
+__device__ __forceinline__ uint2 claim_tile(const GroupArgs &g, const TileMeta &m, u64 n_tiles, int lane) {
+    u64 c = 0;
+    if (lane == 0) c = g.counter_is_remote ? atomicAdd_system(g.next_tile, 1ull) : atomicAdd(g.next_tile, 1ull);
+    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+    const u64 t = c * g.claim_stride + g.claim_offset;
+    if (t >= n_tiles) return make_uint2(NO_TILE, 0u);
+    const uint32_t qb = find_query_block(g.tile_start, m.n_qb, t, lane);
+    RH_CHECK_IDX(qb, m.n_qb);
+    const uint32_t cb = first_cand_block(g.qfile[(size_t)qb * HT_TQ]) + (uint32_t)(t - g.tile_start[qb]);
+    RH_CHECK_IDX(cb, m.n_cb);
+    return make_uint2(qb, cb);
 }
 
 // PF = 0: every pair gets the full 256-bit distance (dist256).
@@ -124,109 +161,155 @@ __global__ void tile_list_kernel(const uint32_t *tile_start, const uint32_t *qfi
 // same exact slow path.  Results are identical to PF = 0 for any input.
 template <int PF>
 __global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const GroupArgs g) {
-    uint32_t cb, qb;
-    if (!decode_tile(g, qb, cb)) return;
-    const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
-    const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
-
-    __shared__ uint4 s_cand[HT_TC * 2];
+    __shared__ __align__(128) uint4 s_cand[2][HT_TC * 2];
     __shared__ GroupArgs s_g;
-    if (threadIdx.x == 0) s_g = g;
-    const uint4 *cand4 = reinterpret_cast<const uint4 *>(g.cand) + (size_t)c0 * 2;
-    for (int i = threadIdx.x; i < HT_TC * 2; i += HT_THREADS) s_cand[i] = cand4[i];
+    __shared__ TileSched s_sched;
+    const TileMeta m = *g.meta;
+    const u64 n_tiles = g.tile_start[g.n_qb_max];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_g = g;
+        s_g.nc = m.nc;
+        rh::mbar_init(&s_sched.bar[0], 1);
+        rh::mbar_init(&s_sched.bar[1], 1);
+        rh::mbar_fence_init();
+    }
+    __syncthreads();
+    constexpr uint32_t STAGE_BYTES = HT_TC * 32;
+    const uint4 *cand4 = reinterpret_cast<const uint4 *>(g.cand);
+    auto stage = [&](int buf) {   // warp 0
+        const uint2 t = claim_tile(g, m, n_tiles, lane);
+        if (lane == 0) {
+            s_sched.tile[buf] = t;
+            if (t.x != NO_TILE) {
+                rh::mbar_arrive_expect_tx(&s_sched.bar[buf], STAGE_BYTES);
+                rh::bulk_g2s(s_cand[buf], cand4 + (size_t)t.y * (HT_TC * 2), STAGE_BYTES, &s_sched.bar[buf]);
+            }
+        }
+    };
+    if (warp == 0) stage(0);
+    __syncthreads();
 
     uint32_t q[HT_RQ][8];
     uint32_t qf[HT_RQ];
-#pragma unroll
-    for (int r = 0; r < HT_RQ; r++) {
-        const uint32_t row = q0 + r * HT_THREADS + threadIdx.x;
-        const uint4 *p = reinterpret_cast<const uint4 *>(g.qry) + (size_t)row * 2;
-        uint4 a = p[0], b = p[1];
-        q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w;
-        q[r][4] = b.x; q[r][5] = b.y; q[r][6] = b.z; q[r][7] = b.w;
-        qf[r] = g.qfile[row];
-    }
-    __syncthreads();
-
+    uint32_t cur_qb = NO_TILE;
     const uint32_t T = g.threshold;
-    const int cn = (int)(c1 - c0);
     uint32_t local_edges = 0;
+    for (uint32_t it = 0;; it++) {
+        const int buf = (int)(it & 1u);
+        const uint2 tile = s_sched.tile[buf];
+        if (tile.x == NO_TILE) break;
+        // the other stage was last read in the previous iteration, which ended with a barrier
+        if (warp == 0) stage(buf ^ 1);
+        if (tile.x != cur_qb) {
+            cur_qb = tile.x;
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) {
+                const uint32_t row = cur_qb * HT_TQ + r * HT_THREADS + threadIdx.x;
+                const uint4 *p = reinterpret_cast<const uint4 *>(g.qry) + (size_t)row * 2;
+                uint4 a = p[0], b = p[1];
+                q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w;
+                q[r][4] = b.x; q[r][5] = b.y; q[r][6] = b.z; q[r][7] = b.w;
+                qf[r] = g.qfile[row];
+            }
+        }
+        const uint32_t c0 = tile.y * HT_TC;
+        const int cn = (int)(min(c0 + (uint32_t)HT_TC, m.nc) - c0);
+        rh::mbar_wait(&s_sched.bar[buf], (it >> 1) & 1u);
+        const uint4 *sc = s_cand[buf];
 #pragma unroll 2
-    for (int c = 0; c < cn; c++) {
-        const uint4 a = s_cand[2 * c];
-        uint32_t d[HT_RQ];
-        if (PF == 0) {
-            const uint4 b = s_cand[2 * c + 1];
+        for (int c = 0; c < cn; c++) {
+            const uint4 a = sc[2 * c];
+            uint32_t d[HT_RQ];
+            if (PF == 0) {
+                const uint4 b = sc[2 * c + 1];
 #pragma unroll
-            for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
-        } else {
+                for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+            } else {
 #pragma unroll
-            for (int r = 0; r < HT_RQ; r++) {
-                const uint32_t x0 = q[r][0] ^ a.x, x1 = q[r][1] ^ a.y, x2 = q[r][2] ^ a.z;
-                // p(s) + 2 p(c) as one IMAD: keeps the add off the (busier) LOP3/IADD pipe
-                asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d[r]) : "r"(__popc(maj3(x0, x1, x2))), "r"(__popc(xor3(x0, x1, x2))));
-                if (PF == 4) d[r] += __popc(q[r][3] ^ a.w);
-            }
-        }
-        uint32_t m = d[0];
-#pragma unroll
-        for (int r = 1; r < HT_RQ; r++) m = min(m, d[r]);
-        if (m <= T) {
-            const uint4 b = s_cand[2 * c + 1];
-#pragma unroll
-            for (int r = 0; r < HT_RQ; r++) {
-                if (d[r] > T) continue;
-                uint32_t full = d[r];
-                if (PF != 0) {
-                    if (PF == 3) full += __popc(q[r][3] ^ a.w);
-                    full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
-                            __popc(q[r][7] ^ b.w);
+                for (int r = 0; r < HT_RQ; r++) {
+                    const uint32_t x0 = q[r][0] ^ a.x, x1 = q[r][1] ^ a.y, x2 = q[r][2] ^ a.z;
+                    // p(s) + 2 p(c) as one IMAD: keeps the add off the (busier) LOP3/IADD pipe
+                    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d[r]) : "r"(__popc(maj3(x0, x1, x2))), "r"(__popc(xor3(x0, x1, x2))));
+                    if (PF == 4) d[r] += __popc(q[r][3] ^ a.w);
                 }
-                if (full <= T) local_edges += slow_hit(&s_g, full, qf[r], c0 + c);
+            }
+            uint32_t mn = d[0];
+#pragma unroll
+            for (int r = 1; r < HT_RQ; r++) mn = min(mn, d[r]);
+            if (mn <= T) {
+                const uint4 b = sc[2 * c + 1];
+#pragma unroll
+                for (int r = 0; r < HT_RQ; r++) {
+                    if (d[r] > T) continue;
+                    uint32_t full = d[r];
+                    if (PF != 0) {
+                        if (PF == 3) full += __popc(q[r][3] ^ a.w);
+                        full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
+                                __popc(q[r][7] ^ b.w);
+                    }
+                    if (full <= T) local_edges += slow_hit(&s_g, full, qf[r], c0 + c);
+                }
             }
         }
+        __syncthreads();   // everyone is done with this stage; the next tile's description is visible
     }
     // one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_edges += __shfl_xor_sync(0xFFFFFFFFu, local_edges, o);
-    if ((threadIdx.x & 31) == 0 && local_edges) atomicAdd(g.edge_count, (unsigned long long)local_edges);
+    if (lane == 0 && local_edges) atomicAdd(g.edge_count, (u64)local_edges);
 }
 
-// 64-bit hashes (hamminghash.rs:23-41): 2 words per hash, one thread per query row, the same
-// tile ownership.  Throughput is not a target here (no reference caller groups u64 hashes).
+// 64-bit hashes (hamminghash.rs:23-41): 2 words per hash, the same persistent tile pool; the 4 KB of
+// candidates per tile are loaded directly.  Throughput is not a target here (no reference caller
+// groups u64 hashes).
 __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_u64_kernel(const GroupArgs g) {
-    uint32_t cb, qb;
-    if (!decode_tile(g, qb, cb)) return;
-    const uint32_t q0 = qb * HT_TQ, c0 = cb * HT_TC;
-    const uint32_t c1 = min(c0 + (uint32_t)HT_TC, g.nc);
     __shared__ uint2 s_cand[HT_TC];
     __shared__ GroupArgs s_g;
-    if (threadIdx.x == 0) s_g = g;
-    const uint2 *cand2 = reinterpret_cast<const uint2 *>(g.cand) + c0;
-    for (int i = threadIdx.x; i < HT_TC; i += HT_THREADS) s_cand[i] = cand2[i];
-    uint2 q[HT_RQ];
-    uint32_t qf[HT_RQ];
-#pragma unroll
-    for (int r = 0; r < HT_RQ; r++) {
-        const uint32_t row = q0 + r * HT_THREADS + threadIdx.x;
-        q[r] = reinterpret_cast<const uint2 *>(g.qry)[row];
-        qf[r] = g.qfile[row];
+    __shared__ uint2 s_tile;
+    const TileMeta m = *g.meta;
+    const u64 n_tiles = g.tile_start[g.n_qb_max];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_g = g;
+        s_g.nc = m.nc;
     }
-    __syncthreads();
     const uint32_t T = g.threshold;
-    const int cn = (int)(c1 - c0);
     uint32_t local_edges = 0;
-    for (int c = 0; c < cn; c++) {
-        const uint2 a = s_cand[c];
+    for (;;) {
+        __syncthreads();   // the previous tile's candidates and description are no longer needed
+        if (warp == 0) {
+            const uint2 t = claim_tile(g, m, n_tiles, lane);
+            if (lane == 0) s_tile = t;
+        }
+        __syncthreads();
+        const uint2 tile = s_tile;
+        if (tile.x == NO_TILE) break;
+        const uint32_t q0 = tile.x * HT_TQ, c0 = tile.y * HT_TC;
+        const int cn = (int)(min(c0 + (uint32_t)HT_TC, m.nc) - c0);
+        const uint2 *cand2 = reinterpret_cast<const uint2 *>(g.cand) + c0;
+        for (int i = threadIdx.x; i < HT_TC; i += HT_THREADS) s_cand[i] = cand2[i];
+        uint2 q[HT_RQ];
+        uint32_t qf[HT_RQ];
 #pragma unroll
         for (int r = 0; r < HT_RQ; r++) {
-            uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
-            if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+            const uint32_t row = q0 + r * HT_THREADS + threadIdx.x;
+            q[r] = reinterpret_cast<const uint2 *>(g.qry)[row];
+            qf[r] = g.qfile[row];
+        }
+        __syncthreads();
+        for (int c = 0; c < cn; c++) {
+            const uint2 a = s_cand[c];
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) {
+                uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
+                if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+            }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_edges += __shfl_xor_sync(0xFFFFFFFFu, local_edges, o);
-    if ((threadIdx.x & 31) == 0 && local_edges) atomicAdd(g.edge_count, (unsigned long long)local_edges);
+    if (lane == 0 && local_edges) atomicAdd(g.edge_count, (u64)local_edges);
 }
 
 // ------------------------------------------------------------ preparation ----
@@ -246,6 +329,18 @@ __global__ void flags_kernel(const uint8_t *has_hash, const uint8_t *n_variants,
     nv[i] = q;
 }
 
+// the scans' totals -> TileMeta; zeroes the edge counter, the edge-list fill and the claim counter
+__global__ void meta_kernel(const uint32_t *dpos, const uint32_t *qoff, uint32_t n, TileMeta *meta, u64 *counters) {
+    const uint32_t nc = dpos[n], nq = qoff[n];
+    meta->nc = nc;
+    meta->nq = nq;
+    meta->n_qb = (nq + HT_TQ - 1) / HT_TQ;
+    meta->n_cb = (nc + HT_TC - 1) / HT_TC;
+    counters[0] = 0;   // comparison_count
+    counters[1] = 0;   // edges written to the optional sink
+    counters[2] = 0;   // next tile to claim (unused when the group's shared counter is given)
+}
+
 __device__ __forceinline__ uint32_t load_le32(const uint8_t *p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
@@ -257,8 +352,8 @@ __global__ void scatter_kernel(const uint8_t *hashes, const uint8_t *variants, c
                                uint32_t n, const uint32_t *valid, const uint32_t *dpos,
                                const uint32_t *nv, const uint32_t *qoff, uint32_t *cand,
                                uint32_t *cand_idx, uint8_t *lc, uint32_t *qry, uint32_t *qfile) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t i = t / W, w = t % W;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const uint32_t i = (uint32_t)(t / W), w = (uint32_t)(t % W);
     if (i >= n || !valid[i]) return;
     const uint32_t k = dpos[i];
     cand[(size_t)k * W + w] = load_le32(hashes + (size_t)i * (W * 4) + w * 4);
@@ -274,15 +369,36 @@ __global__ void scatter_kernel(const uint8_t *hashes, const uint8_t *variants, c
     }
 }
 
-// number of candidate blocks that can hold a pair with j > i, per query block (entry n_qb = 0 so
-// that the exclusive scan ends with the total)
-__global__ void tile_counts_kernel(const uint32_t *qfile, uint32_t nc, uint32_t n_qb, uint32_t n_cb, uint32_t *counts) {
-    uint32_t qb = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qb > n_qb) return;
-    uint32_t c = 0;
-    if (qb < n_qb) {
+// the rows between the dense totals and the next block boundary: candidates zero, query rows 0xFF
+// (their qfile = 0xFFFFFFFF makes slow_hit reject them), so that tiles never need a row mask
+template <int W>
+__global__ void pad_kernel(const TileMeta *meta, uint32_t *cand, uint32_t *qry, uint32_t *qfile) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t row = t / W, w = t % W;
+    const TileMeta m = *meta;
+    if (row < (uint32_t)HT_TQ) {
+        const size_t r = (size_t)m.nq + row;
+        if (r < (size_t)m.n_qb * HT_TQ) {
+            qry[r * W + w] = 0xFFFFFFFFu;
+            if (w == 0) qfile[r] = 0xFFFFFFFFu;
+        }
+    }
+    if (row < (uint32_t)HT_TC) {
+        const size_t r = (size_t)m.nc + row;
+        if (r < (size_t)m.n_cb * HT_TC) cand[r * W + w] = 0u;
+    }
+}
+
+// number of candidate blocks that can hold a pair with j > i, per query block (entries from
+// meta.n_qb to n_qb_max are 0, so the exclusive scan ends with the total)
+__global__ void tile_counts_kernel(const uint32_t *qfile, const TileMeta *meta, uint32_t n_qb_max, u64 *counts) {
+    const uint32_t qb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qb > n_qb_max) return;
+    const TileMeta m = *meta;
+    u64 c = 0;
+    if (qb < m.n_qb) {
         const uint32_t f0 = qfile[(size_t)qb * HT_TQ];
-        if (f0 != 0xFFFFFFFFu && f0 + 1u < nc) c = n_cb - min(n_cb, first_cand_block(f0));
+        if (f0 != 0xFFFFFFFFu && f0 + 1u < m.nc) c = m.n_cb - min(m.n_cb, first_cand_block(f0));
     }
     counts[qb] = c;
 }
@@ -325,10 +441,9 @@ __global__ void distances_kernel(const uint8_t *a, const uint8_t *b, size_t n, u
     out[i] = d;
 }
 
-__global__ void edges_to_sparse_kernel(uint2 *edges, unsigned long long cap, const unsigned long long *n_edges,
-                                       const uint32_t *cand_idx) {
-    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    unsigned long long m = *n_edges < cap ? *n_edges : cap;
+__global__ void edges_to_sparse_kernel(uint2 *edges, u64 cap, const u64 *n_edges, const uint32_t *cand_idx) {
+    u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    u64 m = *n_edges < cap ? *n_edges : cap;
     if (k >= m) return;
     uint2 e = edges[k];
     edges[k] = make_uint2(cand_idx[e.x], cand_idx[e.y]);
@@ -359,14 +474,16 @@ __global__ void group_max_dist_kernel(const uint8_t *pivots, const uint8_t *n_pi
 struct Prepared {
     GroupArgs g;
     const uint32_t *valid, *dpos, *cand_idx;
-    uint32_t n_qb, n_cb;
+    u64 *counters;
+    size_t tiles_upper;   // host-side upper bound of the tile count (sizes the persistent grid)
 };
 
-// Builds the dense candidate / query arrays on the device.  W = words per hash (8 or 2).
+// Builds the dense candidate / query arrays on the device; every size the host needs is an upper
+// bound derived from n (the exact totals stay on the device in TileMeta).  W = words per hash.
 template <int W>
 int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
             const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
-            int rank, int world, Prepared *out) {
+            const rh::HammingPlan &plan, Prepared *out) {
     using namespace rh;
     cudaStream_t st = ctx->stream;
     const size_t hb = W * 4;
@@ -377,80 +494,63 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     RH_TRY(stage_in(ctx, n_variants, (size_t)n, S_IN3, &d_nv));
     RH_TRY(stage_in(ctx, low_conf, (size_t)n, S_IN4, &d_lc));
 
+    const size_t nq_max = (size_t)n * (d_var ? 8 : 1);
+    const size_t nc_pad = (size_t)cdiv((size_t)n, HT_TC) * HT_TC;
+    const size_t nq_pad = (size_t)cdiv(nq_max, HT_TQ) * HT_TQ;
+    const uint32_t n_qb_max = (uint32_t)(nq_pad / HT_TQ), n_cb_max = (uint32_t)(nc_pad / HT_TC);
+
     uint32_t *valid, *nv, *dpos, *qoff;
     void *p;
     RH_TRY(scratch(ctx, S_W0, (size_t)(n + 1) * 4, &p)); valid = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W1, (size_t)(n + 1) * 4, &p)); nv = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W2, (size_t)(n + 1) * 4, &p)); dpos = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W3, (size_t)(n + 1) * 4, &p)); qoff = (uint32_t *)p;
-    flags_kernel<<<cdiv(n + 1, 256), 256, 0, st>>>(d_has, d_nv, d_var != nullptr, (uint32_t)n, valid, nv);
-    RH_LAUNCHED(ctx, "flags_kernel");
-    size_t tmp_bytes = 0;
-    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, valid, dpos, (int)(n + 1), st));
-    void *tmp;
-    RH_TRY(scratch(ctx, S_W4, tmp_bytes, &tmp));
-    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, valid, dpos, (int)(n + 1), st));
-    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nv, qoff, (int)(n + 1), st));
-    ctx->launches += 2;
-    uint32_t totals[2];
-    RH_CUDA(ctx, cudaMemcpyAsync(&totals[0], dpos + n, 4, cudaMemcpyDeviceToHost, st));
-    RH_CUDA(ctx, cudaMemcpyAsync(&totals[1], qoff + n, 4, cudaMemcpyDeviceToHost, st));
-    RH_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t nc = totals[0], nq = totals[1];
-    const size_t nc_pad = (size_t)cdiv(nc ? nc : 1, HT_TC) * HT_TC;
-    const size_t nq_pad = (size_t)cdiv(nq ? nq : 1, HT_TQ) * HT_TQ;
-
     uint32_t *cand, *cand_idx, *qry, *qfile, *parent;
     uint8_t *lc = nullptr;
-    unsigned long long *counters;
+    u64 *counters, *tcount, *tstart;
     RH_TRY(scratch(ctx, S_W5, nc_pad * hb, &p)); cand = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W6, nc_pad * 4, &p)); cand_idx = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W7, nq_pad * hb, &p)); qry = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W8, nq_pad * 4, &p)); qfile = (uint32_t *)p;
     RH_TRY(scratch(ctx, S_W9, nc_pad * 4, &p)); parent = (uint32_t *)p;
-    RH_TRY(scratch(ctx, S_W10, 64, &p)); counters = (unsigned long long *)p;
+    RH_TRY(scratch(ctx, S_W10, 128, &p)); counters = (u64 *)p;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(counters + 8);
     if (d_lc) {
         RH_TRY(scratch(ctx, S_W11, nc_pad, &p));
         lc = (uint8_t *)p;
     }
-    RH_CUDA(ctx, cudaMemsetAsync(cand, 0, nc_pad * hb, st));
-    RH_CUDA(ctx, cudaMemsetAsync(qry, 0xFF, nq_pad * hb, st));
-    RH_CUDA(ctx, cudaMemsetAsync(qfile, 0xFF, nq_pad * 4, st));
-    RH_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, st));
-    if (n > 0) {
-        scatter_kernel<W><<<cdiv((size_t)n * W, 256), 256, 0, st>>>(d_hashes, d_var, d_lc, (uint32_t)n, valid, dpos, nv,
-                                                                    qoff, cand, cand_idx, lc, qry, qfile);
-        RH_LAUNCHED(ctx, "scatter_kernel");
-    }
+    RH_TRY(scratch(ctx, S_W12, (size_t)(n_qb_max + 1) * 8, &p)); tcount = (u64 *)p;
+    RH_TRY(scratch(ctx, S_W13, (size_t)(n_qb_max + 1) * 8, &p)); tstart = (u64 *)p;
+    size_t tmp_a = 0, tmp_b = 0;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, valid, dpos, (int)(n + 1), st));
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, tcount, tstart, (int)(n_qb_max + 1), st));
+    const size_t tmp_bytes = tmp_a > tmp_b ? tmp_a : tmp_b;
+    void *tmp;
+    RH_TRY(scratch(ctx, S_W4, tmp_bytes, &tmp));
+
+    flags_kernel<<<cdiv(n + 1, 256), 256, 0, st>>>(d_has, d_nv, d_var != nullptr, (uint32_t)n, valid, nv);
+    RH_LAUNCHED(ctx, "flags_kernel");
+    size_t tb = tmp_bytes;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tb, valid, dpos, (int)(n + 1), st));
+    tb = tmp_bytes;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tb, nv, qoff, (int)(n + 1), st));
+    ctx->launches += 2;
+    meta_kernel<<<1, 1, 0, st>>>(dpos, qoff, (uint32_t)n, meta, counters);
+    RH_LAUNCHED(ctx, "meta_kernel");
+    scatter_kernel<W><<<cdiv((size_t)n * W, 256), 256, 0, st>>>(d_hashes, d_var, d_lc, (uint32_t)n, valid, dpos, nv, qoff,
+                                                                cand, cand_idx, lc, qry, qfile);
+    RH_LAUNCHED(ctx, "scatter_kernel");
+    pad_kernel<W><<<cdiv((size_t)HT_TQ * W, 256), 256, 0, st>>>(meta, cand, qry, qfile);
+    RH_LAUNCHED(ctx, "pad_kernel");
     iota_kernel<<<cdiv(nc_pad, 256), 256, 0, st>>>(parent, (uint32_t)nc_pad);
     RH_LAUNCHED(ctx, "iota_kernel");
-    // the list of tiles that can contain a pair with j > i
-    const uint32_t n_qb = (uint32_t)(nq_pad / HT_TQ), n_cb = (uint32_t)(nc_pad / HT_TC);
-    uint32_t *tcount, *tstart;
-    RH_TRY(scratch(ctx, S_W12, (size_t)(n_qb + 1) * 4, &p)); tcount = (uint32_t *)p;
-    RH_TRY(scratch(ctx, S_W13, (size_t)(n_qb + 1) * 4, &p)); tstart = (uint32_t *)p;
-    tile_counts_kernel<<<cdiv(n_qb + 1, 256), 256, 0, st>>>(qfile, nc, n_qb, n_cb, tcount);
+    tile_counts_kernel<<<cdiv(n_qb_max + 1, 256), 256, 0, st>>>(qfile, meta, n_qb_max, tcount);
     RH_LAUNCHED(ctx, "tile_counts_kernel");
-    size_t tmp2 = 0;
-    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp2, tcount, tstart, (int)(n_qb + 1), st));
-    if (tmp2 > tmp_bytes) RH_TRY(scratch(ctx, S_W4, tmp2, &tmp));
-    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp2, tcount, tstart, (int)(n_qb + 1), st));
+    tb = tmp_bytes;
+    RH_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tb, tcount, tstart, (int)(n_qb_max + 1), st));
     ctx->launches += 1;
-    uint32_t n_tiles = 0;
-    RH_CUDA(ctx, cudaMemcpyAsync(&n_tiles, tstart + n_qb, 4, cudaMemcpyDeviceToHost, st));
-    RH_CUDA(ctx, cudaStreamSynchronize(st));
-
-    uint2 *tlist;
-    RH_TRY(scratch(ctx, S_W14, (size_t)(n_tiles ? n_tiles : 1) * sizeof(uint2), &p)); tlist = (uint2 *)p;
-    if (n_tiles) {
-        tile_list_kernel<<<cdiv(n_tiles, 256), 256, 0, st>>>(tstart, qfile, n_qb, n_tiles, tlist);
-        RH_LAUNCHED(ctx, "tile_list_kernel");
-    }
 
     GroupArgs &g = out->g;
-    g.tile_list = tlist;
-    g.n_qb = n_qb;
-    g.n_tiles = n_tiles;
     g.cand = cand;
     g.qry = qry;
     g.qfile = qfile;
@@ -460,32 +560,43 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     g.edges = nullptr;
     g.edges_cap = 0;
     g.edges_n = counters + 1;
-    g.nc = nc;
-    g.nq = nq;
+    g.meta = meta;
+    g.tile_start = tstart;
+    g.n_qb_max = n_qb_max;
+    if (plan.shared_counter) {   // one pool for every GPU of the group
+        g.next_tile = plan.shared_counter;
+        g.claim_stride = 1;
+        g.claim_offset = 0;
+        g.counter_is_remote = 1;
+    } else {                     // static cyclic ownership: tile t belongs to rank t mod world
+        g.next_tile = counters + 2;
+        g.claim_stride = (uint32_t)plan.world;
+        g.claim_offset = (uint32_t)plan.rank;
+        g.counter_is_remote = 0;
+    }
+    g.nc = 0;
     g.threshold = similarity;
-    g.rank = rank;
-    g.world = world;
     out->valid = valid;
     out->dpos = dpos;
     out->cand_idx = cand_idx;
-    out->n_cb = n_cb;
-    out->n_qb = n_qb;
+    out->counters = counters;
+    out->tiles_upper = (size_t)n_qb_max * n_cb_max;
     return RH_OK;
 }
 
 template <int W>
-int run_tiles(rh_ctx *ctx, const Prepared &pr) {
+int run_tiles(rh_ctx *ctx, const Prepared &pr, int world) {
     cudaStream_t st = ctx->stream;
     ctx->last_ms = 0.0;
     ctx->last_units = 0.0;
-    if (pr.g.nc < 2 || pr.g.nq == 0 || pr.g.n_tiles == 0) return RH_OK;
-    const unsigned grid = rh::cdiv(pr.g.n_tiles, (size_t)pr.g.world);
+    // persistent grid: 4 CTAs per SM, fewer when the whole pool is smaller than that
+    size_t share = pr.tiles_upper / (size_t)(world > 0 ? world : 1) + 1;
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, share);
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
     if (W == 8) {
         // two-stage search when the threshold is low enough for the prefix filter to be selective
-        const char *force = getenv("RH_HAMMING_PREFILTER");   // "0" | "3" | "4": pin the variant (benchmarks)
         int pf = pr.g.threshold <= 32 ? 3 : (pr.g.threshold <= 46 ? 4 : 0);
-        if (force) pf = atoi(force);
+        if (ctx->force_prefilter >= 0) pf = ctx->force_prefilter;   // rh_ctx_set_option (benchmarks)
         if (pf == 3)
             hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
         else if (pf == 4)
@@ -496,10 +607,48 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr) {
         hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
     RH_LAUNCHED(ctx, "hamming_tiles_kernel");
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
-    RH_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
-    float ms = 0.f;
-    RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
-    ctx->last_ms = ms;
+    ctx->timing_pending = true;
+    return RH_OK;
+}
+
+int check_group_args(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *variants, const uint8_t *n_variants, int64_t n,
+                     uint32_t similarity, uint32_t max_similarity, int rank, int world) {
+    using namespace rh;
+    if (n < 0 || n > 0x7FFFFFF0ll) return fail(ctx, RH_EINVAL, "n out of range");
+    if (similarity > max_similarity) return fail(ctx, RH_EINVAL, "similarity above 63 (scanner.rs:1650-1655)");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, RH_EINVAL, "bad rank/world");
+    if ((n > 0 && !hashes) || (n_variants && !variants)) return fail(ctx, RH_EINVAL, "null hashes");
+    // dense ids, query rows and their scans are 32-bit
+    if ((uint64_t)n * (variants ? 8u : 1u) > 0xFFFFF000ull)
+        return fail(ctx, RH_EUNSUPPORTED, "more than 2^32 query rows (n x variants): split the library");
+    return RH_OK;
+}
+
+template <int W>
+int enqueue_impl(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                 const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                 const rh::HammingPlan &plan, uint32_t *d_out_label, uint2 *d_edges, size_t edges_cap,
+                 const u64 **d_counters) {
+    using namespace rh;
+    cudaStream_t st = ctx->stream;
+    Prepared pr;
+    RH_TRY(prepare<W>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, plan, &pr));
+    if (d_edges && edges_cap) {
+        pr.g.edges = d_edges;
+        pr.g.edges_cap = edges_cap;
+    }
+    if (plan.before_tiles) RH_CUDA(ctx, cudaStreamWaitEvent(st, plan.before_tiles, 0));
+    RH_TRY(run_tiles<W>(ctx, pr, plan.shared_counter ? plan.world : plan.world));
+    if (d_out_label) {
+        labels_kernel<<<cdiv(n, 256), 256, 0, st>>>(pr.g.parent, pr.valid, pr.dpos, pr.cand_idx, (uint32_t)n, d_out_label);
+        RH_LAUNCHED(ctx, "labels_kernel");
+    }
+    if (d_edges && edges_cap) {
+        // dense ids -> file indices (the edge list itself is unordered)
+        edges_to_sparse_kernel<<<cdiv(edges_cap, 256), 256, 0, st>>>(pr.g.edges, pr.g.edges_cap, pr.g.edges_n, pr.cand_idx);
+        RH_LAUNCHED(ctx, "edges_to_sparse_kernel");
+    }
+    if (d_counters) *d_counters = pr.counters;
     return RH_OK;
 }
 
@@ -510,45 +659,68 @@ int group_impl(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, cons
                uint32_t *out_edges, size_t edges_cap) {
     using namespace rh;
     if (!ctx) return RH_EINVAL;
-    if (n < 0 || n > 0x7FFFFFF0ll) return fail(ctx, RH_EINVAL, "n out of range");
-    if (similarity > max_similarity) return fail(ctx, RH_EINVAL, "similarity above 63 (scanner.rs:1650-1655)");
-    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, RH_EINVAL, "bad rank/world");
-    if ((n > 0 && !hashes) || (n_variants && !variants)) return fail(ctx, RH_EINVAL, "null hashes");
+    RH_TRY(check_group_args(ctx, hashes, variants, n_variants, n, similarity, max_similarity, rank, world));
     RH_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (out_edge_count) *out_edge_count = 0;
     if (n == 0) return RH_OK;
-    Prepared pr;
-    RH_TRY(prepare<W>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, rank, world, &pr));
-    OutBuf<uint32_t> lab;
+    OutBuf<uint32_t> lab, edg;
     RH_TRY(lab.prepare(ctx, out_label, (size_t)n, S_OUT0));
-    OutBuf<uint32_t> edg;
-    if (out_edges && edges_cap) {
-        RH_TRY(edg.prepare(ctx, out_edges, edges_cap * 2, S_OUT1));
-        pr.g.edges = reinterpret_cast<uint2 *>(edg.dev);
-        pr.g.edges_cap = edges_cap;
-    }
-    RH_TRY(run_tiles<W>(ctx, pr));
-    if (lab.dev) {
-        labels_kernel<<<cdiv(n, 256), 256, 0, st>>>(pr.g.parent, pr.valid, pr.dpos, pr.cand_idx, (uint32_t)n, lab.dev);
-        RH_LAUNCHED(ctx, "labels_kernel");
-        RH_TRY(lab.finish(ctx));
-    }
-    if (edg.dev) {
-        // dense ids -> file indices (the edge list itself is unordered)
-        edges_to_sparse_kernel<<<cdiv(edges_cap, 256), 256, 0, st>>>(pr.g.edges, pr.g.edges_cap, pr.g.edges_n,
-                                                                     pr.cand_idx);
-        RH_LAUNCHED(ctx, "edges_to_sparse_kernel");
-        RH_TRY(edg.finish(ctx));
-    }
-    unsigned long long counts[2] = {0, 0};
-    RH_CUDA(ctx, cudaMemcpyAsync(counts, pr.g.edge_count, 16, cudaMemcpyDeviceToHost, st));
-    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out_edges && edges_cap) RH_TRY(edg.prepare(ctx, out_edges, edges_cap * 2, S_OUT1));
+    HammingPlan plan;
+    plan.rank = rank;
+    plan.world = world;
+    const u64 *d_counters = nullptr;
+    RH_TRY(enqueue_impl<W>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, plan, lab.dev,
+                           reinterpret_cast<uint2 *>(edg.dev), edg.dev ? edges_cap : 0, &d_counters));
+    RH_TRY(lab.finish(ctx));
+    RH_TRY(edg.finish(ctx));
+    u64 counts[2] = {0, 0};
+    RH_CUDA(ctx, cudaMemcpyAsync(counts, d_counters, 16, cudaMemcpyDeviceToHost, st));
+    RH_CUDA(ctx, cudaStreamSynchronize(st));   // the only host synchronisation of a search
+    RH_TRY(finish_timing(ctx));
     if (out_edge_count) *out_edge_count = counts[0];
     return RH_OK;
 }
 
 }  // namespace
+
+namespace rh {
+
+int finish_timing(rh_ctx *ctx) {
+    if (ctx->timing_pending) {
+        float ms = 0.f;
+        RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        ctx->last_ms = ms;
+        ctx->timing_pending = false;
+    }
+    return RH_OK;
+}
+
+int hamming_group_enqueue(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                          const uint8_t *n_variants, const uint8_t *low_conf, int64_t n, uint32_t similarity,
+                          const HammingPlan &plan, uint32_t *d_out_label, const unsigned long long **d_counters) {
+    RH_TRY(check_group_args(ctx, hashes, variants, n_variants, n, similarity, RH_MAX_SIMILARITY_256, plan.rank, plan.world));
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    return enqueue_impl<8>(ctx, hashes, has_hash, variants, n_variants, low_conf, n, similarity, plan, d_out_label, nullptr,
+                           0, d_counters);
+}
+
+int uf_merge_enqueue(rh_ctx *ctx, const uint32_t *d_parents, int world, int64_t n, uint32_t *d_out_label) {
+    cudaStream_t st = ctx->stream;
+    void *p;
+    RH_TRY(scratch(ctx, S_W9, (size_t)n * 4, &p));
+    uint32_t *parent = (uint32_t *)p;
+    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n);
+    RH_LAUNCHED(ctx, "iota_kernel");
+    merge_kernel<<<cdiv((size_t)n * world, 256), 256, 0, st>>>(d_parents, (uint32_t)n, world, parent);
+    RH_LAUNCHED(ctx, "merge_kernel");
+    flatten_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n, d_out_label);
+    RH_LAUNCHED(ctx, "flatten_kernel");
+    return RH_OK;
+}
+
+}  // namespace rh
 
 extern "C" {
 
@@ -581,22 +753,13 @@ int rh_uf_merge(rh_ctx *ctx, const uint32_t *parents, int world, int64_t n, uint
         return fail(ctx, RH_EINVAL, "rh_uf_merge: bad arguments");
     if (n == 0) return RH_OK;
     RH_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const uint32_t *d_par;
     RH_TRY(stage_in(ctx, parents, (size_t)n * world, S_IN0, &d_par));
-    void *p;
-    RH_TRY(scratch(ctx, S_W9, (size_t)n * 4, &p));
-    uint32_t *parent = (uint32_t *)p;
     OutBuf<uint32_t> lab;
     RH_TRY(lab.prepare(ctx, out_label, (size_t)n, S_OUT0));
-    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n);
-    RH_LAUNCHED(ctx, "iota_kernel");
-    merge_kernel<<<cdiv((size_t)n * world, 256), 256, 0, st>>>(d_par, (uint32_t)n, world, parent);
-    RH_LAUNCHED(ctx, "merge_kernel");
-    flatten_kernel<<<cdiv(n, 256), 256, 0, st>>>(parent, (uint32_t)n, lab.dev);
-    RH_LAUNCHED(ctx, "flatten_kernel");
+    RH_TRY(uf_merge_enqueue(ctx, d_par, world, n, lab.dev));
     RH_TRY(lab.finish(ctx));
-    RH_CUDA(ctx, cudaStreamSynchronize(st));
+    RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RH_OK;
 }
 

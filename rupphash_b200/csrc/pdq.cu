@@ -571,7 +571,7 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
     TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
     const bool on_device = is_device_ptr(pixels);
     // host input is staged into 256-byte aligned buffers, so only the pitches matter there
-    const bool fused = pdq_fused_supported(W, H) != 0 && !getenv("RH_PDQ_FORCE_GENERIC") &&
+    const bool fused = pdq_fused_supported(W, H) != 0 && !ctx->pdq_force_generic &&
                        (resize ? (((size_t)W * H) & 15) == 0
                                : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is

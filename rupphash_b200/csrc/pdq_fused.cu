@@ -673,8 +673,8 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &p_p2e));
     FusedArgs a;
     a.p2e = (const float *)p_p2e;
-    // RH_PDQ_PHASE_CLOCKS=1: per-phase cycle totals of thread 0 of every CTA, printed after the kernel
-    const bool clocks = getenv("RH_PDQ_PHASE_CLOCKS") != nullptr;
+    // rh_ctx_set_option("pdq.phase_clocks", 1): per-phase cycle totals of thread 0 of every CTA, printed after the kernel
+    const bool clocks = ctx->pdq_phase_clocks != 0;
     a.phase_clk = nullptr;
     if (clocks) {
         RH_TRY(scratch(ctx, S_W8, NPHASE * sizeof(unsigned long long), &p));
@@ -690,10 +690,8 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     a.dct = d_dct;
     a.out = out;
     a.out_offset = out_offset;
-    const char *pfm = getenv("RH_PDQ_PREFETCH");
-    a.pf_mode = pfm ? atoi(pfm) : 2;
-    const char *pfr = getenv("RH_PDQ_PREFETCH_ROWS");
-    a.pf_rows = pfr ? atoi(pfr) : PF_ROWS;
+    a.pf_mode = ctx->pdq_prefetch;
+    a.pf_rows = ctx->pdq_prefetch_rows;
     const int wc = (H + 63) / 64;
     int rc;
     if (layout == RH_LAYOUT_RGB8)

@@ -193,6 +193,22 @@ def group_files_sharded(hashes, similarity, group=None, has_hash=None, variants=
     return labels, int(total.item())
 
 
+def group_labels_multi(group, hashes, similarity, has_hash=None, variants=None, n_variants=None, low_conf=None,
+                       out=None):
+    """group_labels over every GPU of an rh_group (`_lib.Group`): one process, in-library NCCL over
+    NVLink, tiles claimed by the GPUs from one pool (rh_hamming_group_multi).  Inputs: numpy arrays
+    (ideally page-locked) or CUDA tensors on one GPU of the group.  -> (labels[n], comparison_count),
+    bit-identical to the single-GPU result."""
+    hashes = _u8(hashes)
+    n = int(hashes.shape[0])
+    labels = out if out is not None else np.empty(n, np.uint32)
+    cnt = C.c_uint64()
+    group.check(lib().rh_hamming_group_multi(group.handle, ptr(hashes), ptr(_u8(has_hash)), ptr(_u8(variants)),
+                                             ptr(_u8(n_variants)), ptr(_u8(low_conf)), n, int(similarity),
+                                             ptr(labels), C.byref(cnt)))
+    return labels, int(cnt.value)
+
+
 def merge_groups_by_stem(groups, paths):
     """scanner.rs:1905-1983: groups that contain files with the same parent directory AND the same
     file stem (e.g. IMG_1.jpg / IMG_1.cr2) are merged.  Host logic on paths; returns the groups in

@@ -226,7 +226,7 @@ def test_find_groups_star_vs_oracle(ctx, orc):
     assert [sorted(g) for g in got] == [sorted(g) for g in want]
 
 
-def test_prefilter_variants_agree(ctx, orc, monkeypatch):
+def test_prefilter_variants_agree(ctx, orc):
     """The two-stage (prefix lower bound + refine) kernels and the full-distance kernel are the
     same function: identical labels, edge counts and edge multisets at the bench threshold."""
     from rupphash_b200 import scanner
@@ -235,11 +235,14 @@ def test_prefilter_variants_agree(ctx, orc, monkeypatch):
     hashes[5000:5200, 12:] = hashes[100, 12:]     # pairs that pass the 96-bit prefix test but fail the full one
     hashes[6000:6100, :12] = hashes[200, :12]     # prefix-identical, full distance large
     ref_labels, ref_cnt, _ = orc.group_generic(hashes, 31, low_conf=low_conf, threads=4)
-    for pf in ("0", "3", "4"):
-        monkeypatch.setenv("RH_HAMMING_PREFILTER", pf)
-        labels, cnt = scanner.group_labels(hashes, 31, low_conf=low_conf, ctx=ctx)
-        assert cnt == ref_cnt, pf
-        assert np.array_equal(labels, ref_labels), pf
+    try:
+        for pf in (0, 3, 4):
+            ctx.set_option("hamming.prefilter", pf)
+            labels, cnt = scanner.group_labels(hashes, 31, low_conf=low_conf, ctx=ctx)
+            assert cnt == ref_cnt, pf
+            assert np.array_equal(labels, ref_labels), pf
+    finally:
+        ctx.set_option("hamming.prefilter", -1)
 
 
 def test_group_max_dist_matches_reference_rule(ctx, orc):
