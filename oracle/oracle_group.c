@@ -286,6 +286,7 @@ typedef struct {
     u32vec *chunk_edges; /* per 2000-file chunk, (u,v) interleaved */
     size_t n_chunks;
     size_t next;
+    size_t chunk_stride; /* 1 = every 2000-file chunk (the reference); k > 1: a bounded sample, every k-th chunk */
     pthread_mutex_t mu;
 } grp_job;
 
@@ -314,7 +315,8 @@ static void *grp_worker(void *arg) {
     uint8_t variants_buf[8 * 32];
     for (;;) {
         pthread_mutex_lock(&j->mu);
-        size_t chunk = j->next++;
+        size_t chunk = j->next;
+        j->next += j->chunk_stride ? j->chunk_stride : 1;
         pthread_mutex_unlock(&j->mu);
         if (chunk >= j->n_chunks) break;
         u32vec *edges = &j->chunk_edges[chunk];
@@ -399,10 +401,33 @@ static void labels_from_parent(size_t *parent, size_t n, uint32_t *out_label) {
     free(min_of_root);
 }
 
+static int group_generic_impl(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                              const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
+                              int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
+                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride);
+
 int orc_group_generic(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                       const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
                       int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
                       uint32_t *edges_out, size_t edges_cap) {
+    return group_generic_impl(hashes, has_hash, variants, n_variants, low_conf, n, similarity, threads, use_mih,
+                              out_label, out_edge_count, edges_out, edges_cap, 1);
+}
+
+/* Timing aid for bench.py's cpu_baseline on inputs whose full CPU search takes minutes: the same index
+ * build and probe loop, but only every chunk_stride-th 2000-file chunk of query files is searched
+ * (labels then describe that sample's edges only; the caller scales the probe time by the stride). */
+int orc_group_generic_sampled(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                              const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
+                              int threads, size_t chunk_stride, uint32_t *out_label, uint64_t *out_edge_count) {
+    return group_generic_impl(hashes, has_hash, variants, n_variants, low_conf, n, similarity, threads, 1, out_label,
+                              out_edge_count, NULL, 0, chunk_stride < 1 ? 1 : chunk_stride);
+}
+
+static int group_generic_impl(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
+                              const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
+                              int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
+                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride) {
     if (similarity > 63) return -1; /* assert scanner.rs:1650-1655 */
     for (size_t i = 0; i < n; i++) out_label[i] = (uint32_t)i;
     *out_edge_count = 0;
@@ -428,6 +453,7 @@ int orc_group_generic(const uint8_t *hashes, const uint8_t *has_hash, const uint
     job.mih = use_mih ? orc_mih_new(dense_hashes, n_valid, 256) : NULL; /* :1673 */
     job.dense_to_sparse = dense_to_sparse;
     job.n_chunks = (n + CHUNK_SIZE - 1) / CHUNK_SIZE;
+    job.chunk_stride = chunk_stride;
     job.chunk_edges = (u32vec *)calloc(job.n_chunks + 1, sizeof(u32vec));
     pthread_mutex_init(&job.mu, NULL);
     if (threads < 1) threads = 1;
@@ -471,7 +497,7 @@ int orc_group_generic(const uint8_t *hashes, const uint8_t *has_hash, const uint
  * that have a hash.  A tile (qb, cb) is VALID when its largest candidate index
  * exceeds the file index of its first query (otherwise no j > i pair can exist).
  * Valid tiles are numbered row-major; tile t belongs to rank t % world.
- * This is the same plan rh_hamming_tile_plan() (include/rupphash_b200.h) exposes.
+ * (The device search owns tiles the same way when its ranks are static: tile t -> rank t % world.)
  */
 int orc_group_tiles_rank(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                          const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
