@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: batched PDQ hashing throughput
-(BASELINE.json configs[1]: 1024x768 RGB8 images) plus, reported in the same JSON line, the
-all-pairs Hamming grouping of 500k hashes (configs[2]).
+(BASELINE.json configs[1]: 1024x768 RGB8 images) plus, in the same JSON line, the all-pairs Hamming
+grouping of 500k hashes (configs[2]) with its strong scaling over the GPUs of the box, the worst-case
+inputs of the two-stage search, and the 1M-file pipeline (configs[4]: 1M hashes x 8 dihedral variants).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
     python bench.py --impl reference --gpus N --steps K ...   # the CPU path on the host cores
@@ -9,7 +10,10 @@ all-pairs Hamming grouping of 500k hashes (configs[2]).
 A "step" is one pass of the hashing hot path over one batch of `--batch` synthetic images.
 `value` is device-resident throughput (inputs in HBM before the timed region); `e2e` is the same
 metric through the public API with pinned HOST buffers (H2D of the pixels and D2H of the hashes
-inside the timed region).  One process per GPU; for N > 1 launch under torchrun.
+inside the timed region).  One process per GPU; for N > 1 launch under torchrun.  The Hamming search
+is measured on two routes: one process per GPU + torch.distributed (rh_hamming_group_shard), and ONE
+process driving all N GPUs through the C ABI alone (rh_group: in-library NCCL, tiles stolen over
+NVLink) -- rank 0 runs the second route while the other ranks wait on the host.
 """
 from __future__ import annotations
 
@@ -31,6 +35,13 @@ ALGO_BYTES_PER_IMAGE = IMG_H * IMG_W * IMG_C + 36   # pixels read + 3
 HAMMING_N = 500_000                            # BASELINE.json configs[2]
 HAMMING_T = 31
 POPC_PER_PAIR = 8                              # algorithmic POPC.32 per 256-bit pair
+# POPC.32 the tile kernel executes per pair in its hot loop, by variant (hamming.cu)
+EXEC_POPC = {3: 2, 4: 3, 0: 4}
+EXEC_LOP3 = {3: 5, 4: 6, 0: 16}
+
+# identical in both arms (the driver compares the two `config` objects)
+CONFIG = {"workload": "configs[1]: batched PDQ hashing of synthetic 1024x768 RGB8 images",
+          "image": [IMG_H, IMG_W, IMG_C]}
 
 
 def parse():
@@ -44,7 +55,11 @@ def parse():
     ap.add_argument("--host-pool", type=int, default=256, help="distinct images in the pinned host pool")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--hamming-n", type=int, default=HAMMING_N)
+    ap.add_argument("--config5-n", type=int, default=1_000_000)
+    ap.add_argument("--worstcase-n", type=int, default=200_000)
     ap.add_argument("--skip-hamming", action="store_true")
+    ap.add_argument("--skip-worstcase", action="store_true")
+    ap.add_argument("--skip-config5", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-peaks", action="store_true")
     return ap.parse_args()
@@ -76,10 +91,8 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[0].isdigit() else gpu_index
             self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(gpu_index))
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self._h = None
@@ -119,6 +132,55 @@ class ClockSampler:
                     "source": "nvidia-smi (after the timed region)"}
         except Exception:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+
+
+def physical_index(gpu_index: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    return int(vis.split(",")[gpu_index]) if vis and vis.split(",")[0].isdigit() else gpu_index
+
+
+def pin_to_gpu_numa_node(gpu_index: int) -> dict:
+    """Bind this process (and, by first touch, the pinned pools it allocates afterwards) to the NUMA node
+    the GPU's PCIe root hangs off, so that every rank's H2D traffic stays on its own socket."""
+    info = {"node": None, "cpus": None}
+    global _ALL_CPUS
+    _ALL_CPUS = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(gpu_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["pci"] = bus
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(node=node, cpus=len(allowed))
+    except Exception as e:   # not fatal: the numbers are then simply unpinned
+        info["error"] = str(e)[:80]
+    return info
+
+
+_ALL_CPUS = None
+
+
+def unpin_cpus():
+    """The CPU baselines use every host core, as the reference's rayon pool would."""
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except OSError:
+            pass
 
 
 def synth_pool_device(torch, count, seed):
@@ -167,14 +229,69 @@ def run_reference(args, emit):
         "impl": "reference", "metric": "pdq_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batched PDQ hashing of 1024x768 RGB8 images (CPU oracle port of "
-                               "pdqhash.rs, one image per task over all host threads)",
-                   "images_per_step": per_step, "image": [IMG_H, IMG_W, IMG_C]},
+        "config": dict(CONFIG),
+        "run": {"images_per_step": per_step, "how": "CPU oracle port of pdqhash.rs, one image per task over all host threads"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} images/step x {args.steps} steps"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------- datasets ----
+
+def dihedral_coeff_dataset(torch, ctx, n, seed):
+    """configs[3]/[4] grouping input with REAL dihedral variants: n coefficient blocks (16 x 16 f32, spread
+    falling with frequency like a photo's DCT) -> rh_pdq_dihedral_from_coeffs -> 8 variants per file
+    (scanner.rs:1615-1628), hash = variant 0.  Planted structure: ~2 % of the files are near-copies of another
+    file's coefficients *after one of the 8 dihedral transforms* (sign flips by frequency parity and / or a
+    transpose, pdqhash.rs:71-87), so they match one of the source's variants, not its plain hash; 2 % of the
+    files are low-confidence.  Returns device tensors (hashes n x 32, variants n x 8 x 32, low_conf n)."""
+    from rupphash_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    fr = torch.arange(1, 17, device=dev, dtype=torch.float32)
+    scale = 40.0 / torch.sqrt(fr[:, None] ** 2 + fr[None, :] ** 2)
+    coeffs = torch.randn((n, 16, 16), generator=g, device=dev) * scale
+    k = max(2, n // 50)
+    perm = torch.randperm(n, generator=g, device=dev)
+    src, dst = perm[:k], perm[k:2 * k]
+    t = torch.randint(0, 8, (k,), generator=g, device=dev)
+    c = coeffs[src].clone()
+    odd = (torch.arange(16, device=dev) % 2 == 0).float() * -2.0 + 1.0   # -1 where the frequency r+1 / c+1 is odd
+    neg_rows = ((t == 1) | (t == 2) | (t == 5) | (t == 7))[:, None, None]
+    neg_cols = ((t == 2) | (t == 3) | (t == 4) | (t == 7))[:, None, None]
+    c = torch.where(neg_rows, c * odd[None, :, None], c)
+    c = torch.where(neg_cols, c * odd[None, None, :], c)
+    tr = ((t == 1) | (t == 3) | (t == 6) | (t == 7))[:, None, None]
+    c = torch.where(tr, c.transpose(1, 2), c)
+    coeffs[dst] = c + torch.randn(c.shape, generator=g, device=dev) * 0.05 * scale
+    coeffs = coeffs.reshape(n, 256).contiguous()
+    variants = torch.empty((n, 8, 32), dtype=torch.uint8, device=dev)
+    ctx.check(_lib.lib().rh_pdq_dihedral_from_coeffs(ctx.handle, coeffs.data_ptr(), n, variants.data_ptr()))
+    hashes = variants[:, 0, :].contiguous()
+    low_conf = (torch.rand((n,), generator=g, device=dev) < 0.02).to(torch.uint8)
+    del coeffs
+    return hashes, variants, low_conf
+
+
+def correlated_pdq_hashes(torch, ctx, n, seed):
+    """Hashes with the bit correlations of real PDQ output: smooth random 64 x 64 buffers (a low-frequency
+    field + a little noise) through the real quality / DCT / median tail (rh_pdq_from_buffer64)."""
+    from rupphash_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    slab = 16384
+    for s in range(0, n, slab):
+        m = min(slab, n - s)
+        low = torch.randn((m, 1, 6, 6), generator=g, device=dev) * 40.0
+        buf = torch.nn.functional.interpolate(low, size=(64, 64), mode="bilinear", align_corners=False)[:, 0]
+        buf = (buf + torch.randn((m, 64, 64), generator=g, device=dev) * 2.0 + 128.0).contiguous()
+        ctx.check(_lib.lib().rh_pdq_from_buffer64(ctx.handle, buf.data_ptr(), m, out[s:s + m].data_ptr(), None, None, None))
+    return out
 
 
 def main():
@@ -193,21 +310,27 @@ def main():
     if args.impl == "reference":
         return run_reference(args, emit)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = pin_to_gpu_numa_node(local_rank)   # before any pinned allocation (first touch)
+
     import torch
     import torch.distributed as dist
 
     from rupphash_b200 import _lib, pdqhash, scanner
     from rupphash_b200.synth import planted_hashes
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; rupphash_b200 has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side rendezvous for the phases in which rank 0 alone drives every GPU: the waiting ranks
+        # must not park a spinning NCCL kernel on a GPU rank 0 is using
+        host_group = dist.new_group(backend="gloo")
     ctx = _lib.Context(local_rank)
     # a dedicated non-default stream shared by torch, NCCL and the library, so that the CUDA
     # events below are recorded on the stream the kernels are launched on
@@ -219,6 +342,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -281,10 +409,8 @@ def main():
     pdqhash.hash_batch(host_np, ctx=ctx)      # warm-up (allocates staging)
     barrier()
     t0 = time.perf_counter()
-    ev0.record(stream)
     for _ in range(e2e_steps):
         res = pdqhash.hash_batch(host_np, ctx=ctx)   # H2D pixels + kernels + D2H hash/quality/valid
-    ev1.record(stream)
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * Be * e2e_steps / e2e_wall
@@ -297,11 +423,10 @@ def main():
         "metric": "pdq_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batched PDQ hashing of synthetic 1024x768 RGB8 images, "
-                               "device-resident pool cycled per step",
-                   "images_per_step_per_gpu": B, "image": [IMG_H, IMG_W, IMG_C],
-                   "l2_policy": f"inputs larger than L2: {B * IMG_H * IMG_W * IMG_C / 1e9:.2f} GB read per step",
-                   "parallelism": f"independent batches per GPU x{world} (no collective)"},
+        "config": dict(CONFIG),
+        "run": {"images_per_step_per_gpu": B, "pool": "device-resident pool cycled per step",
+                "l2_policy": f"inputs larger than L2: {B * IMG_H * IMG_W * IMG_C / 1e9:.2f} GB read per step",
+                "parallelism": f"independent batches per GPU x{world} (no collective)", "numa": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "images_per_step_per_gpu": Be, "steps": e2e_steps,
@@ -318,14 +443,26 @@ def main():
     }
 
     # ------------------------------------------------------------- integer / copy peaks -----
+    # every rank measures at the same time: the pinned-H2D figure is then the CONCURRENT rate each GPU gets
+    # while its neighbours copy too -- the denominator of the N-GPU e2e number (a solo figure cannot tell a
+    # shared-uplink limit from a software problem)
     pk = None
-    if not args.skip_peaks and rank == 0:
+    if not args.skip_peaks:
+        barrier()
         pk = ctx.measure_peaks()
-        line["measured_peaks"] = pk
-        if pk["h2d_gbs"] > 0:
-            line["e2e"]["h2d_roofline_frac"] = (e2e_value / world) * IMG_H * IMG_W * IMG_C / 1e9 / pk["h2d_gbs"]
+        h2d_all = [pk["h2d_gbs"]]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, pk["h2d_gbs"], group=host_group)
+            h2d_all = [float(x) for x in gathered]
+        line["measured_peaks"] = dict(pk, h2d_gbs_concurrent_per_rank=h2d_all, h2d_gbs_concurrent_sum=sum(h2d_all))
+        if sum(h2d_all) > 0:
+            line["e2e"]["h2d_roofline_frac"] = e2e_value * IMG_H * IMG_W * IMG_C / 1e9 / sum(h2d_all)
+            line["e2e"]["h2d_roofline_note"] = ("whole-job pixel bytes/s over the sum of the pinned H2D rates all ranks "
+                                                "measured at the same time")
 
     # ------------------------------------------------------------- Hamming grouping --------
+    labels = None
     if not args.skip_hamming:
         n = args.hamming_n
         hashes, low_conf = planted_hashes(n, seed=0xB200, n_clusters=5000, identical_block=1000,
@@ -336,23 +473,18 @@ def main():
 
         def group_device():
             if world == 1:
-                labels, cnt = scanner.group_labels(d_hashes, HAMMING_T, low_conf=d_lc, ctx=ctx)
-                return labels, cnt, ctx.last_kernel_time()[0]
+                lab, cnt = scanner.group_labels(d_hashes, HAMMING_T, low_conf=d_lc, ctx=ctx)
+                return lab, cnt, ctx.last_kernel_time()[0]
             parent, cnt = scanner.group_shard(d_hashes, HAMMING_T, rank, world, low_conf=d_lc, ctx=ctx)
             kms = ctx.last_kernel_time()[0]
             gathered = torch.empty((world, n), dtype=parent.dtype, device="cuda")
             dist.all_gather_into_tensor(gathered, parent)
             total = torch.tensor([cnt], dtype=torch.int64, device="cuda")
             dist.all_reduce(total)
-            labels = scanner.merge_forests(gathered, ctx)
-            return labels, int(total.item()), kms
+            lab = scanner.merge_forests(gathered, ctx)
+            return lab, int(total.item()), kms
 
-        # the full-distance variant (8 words per pair, no prefix filter) for reference
-        os.environ["RH_HAMMING_PREFILTER"] = "0"
-        group_device()
-        _, _, full_ms = group_device()
-        full_ms = max_over_ranks(full_ms)
-        del os.environ["RH_HAMMING_PREFILTER"]
+        # route A: one process per GPU (this process is one rank), static tile ownership
         group_device()
         barrier()
         reps = 3
@@ -364,45 +496,57 @@ def main():
         barrier()
         wall_dev = max_over_ranks((time.perf_counter() - t0) / reps)
         tile_ms = max_over_ranks(kms_sum / reps)
-        # end to end: hashes in pinned host memory -> labels in host memory
-        h_hashes = torch.from_numpy(hashes).pin_memory()
-        h_lc = torch.from_numpy(low_conf).pin_memory()
-        h_labels = torch.empty(n, dtype=torch.int32).pin_memory()
-        barrier()
-        t0 = time.perf_counter()
-        d_hashes.copy_(h_hashes, non_blocking=True)
-        d_lc.copy_(h_lc, non_blocking=True)
-        labels, edges2, _ = group_device()
-        h_labels.copy_(labels if torch.is_tensor(labels) else torch.from_numpy(np.asarray(labels).view(np.int32)))
-        barrier()
-        wall_e2e = max_over_ranks(time.perf_counter() - t0)
+        # the full-distance variant (8 words per pair, no prefix filter) for reference
+        ctx.set_option("hamming.prefilter", 0)
+        group_device()
+        _, _, full_ms = group_device()
+        full_ms = max_over_ranks(full_ms)
+        ctx.set_option("hamming.prefilter", -1)
         ham = {"metric": "hamming_pairs_per_sec", "n_hashes": n, "threshold": HAMMING_T, "pairs": pairs,
                "value": pairs / wall_dev, "unit": "pairs/s", "tile_kernel_ms": tile_ms,
                "tile_kernel_pairs_per_s": pairs / (tile_ms * 1e-3) if tile_ms > 0 else None,
-               "group_wall_ms_device_resident": wall_dev * 1e3, "group_wall_ms_e2e_pinned_host": wall_e2e * 1e3,
-               "edges": int(edges), "edges_e2e": int(edges2), "n_gpus": world,
+               "group_wall_ms_device_resident": wall_dev * 1e3, "edges": int(edges), "n_gpus": world,
+               "route": "one process per GPU (rh_hamming_group / rh_hamming_group_shard + torch.distributed)",
                "kernel_variant": "two-stage: 96-bit prefix lower bound (2 POPC) + exact refine of survivors",
                "full_distance_variant": {"tile_kernel_ms": full_ms,
                                          "pairs_per_s": pairs / (full_ms * 1e-3) if full_ms > 0 else None,
                                          "note": "every pair gets all 8 words: 16 LOP3 + 4 POPC (carry-save)"},
                "exchange": "none (1 GPU)" if world == 1 else "NCCL all-gather of n x u32 forests + all-reduce of edge counts"}
         if pk:
-            peak_pairs = pk["popc_per_s"] / POPC_PER_PAIR
             per_gpu = pairs / world / (tile_ms * 1e-3)
-            ham["roofline"] = {"bound": "int-pipe (POPC.32)", "achieved": per_gpu * POPC_PER_PAIR,
-                               "peak": pk["popc_per_s"], "unit": "POPC/s", "frac": per_gpu / peak_pairs,
-                               "note": "algorithmic 8 POPC per pair over the measured POPC issue rate; the two-stage "
-                                       "kernel executes 2 POPC + 5 LOP3 per pair in its hot loop, so frac exceeds 1",
-                               "executed_popc_frac": per_gpu * 2 / pk["popc_per_s"],
-                               "executed_lop3_frac": per_gpu * 5 / pk["lop3_per_s"],
-                               "full_distance_variant_frac": (pairs / world / (full_ms * 1e-3)) / peak_pairs
-                               if full_ms > 0 else None}
+            ham["roofline"] = {
+                "bound": "int-pipe (POPC.32)", "unit": "POPC/s", "peak": pk["popc_per_s"],
+                "achieved": per_gpu * EXEC_POPC[3], "frac": per_gpu * EXEC_POPC[3] / pk["popc_per_s"],
+                "definition": "POPC.32 the kernel EXECUTES in its hot loop (2 per pair for the 96-bit prefix stage) over "
+                              "the measured POPC issue rate, per GPU; ncu: sm__inst_executed_pipe_xu "
+                              "(profiles/ncu_hamming_tiles_*)",
+                "executed_lop3_frac": per_gpu * EXEC_LOP3[3] / pk["lop3_per_s"],
+                "algorithmic_speedup": POPC_PER_PAIR / EXEC_POPC[3],
+                "algorithmic_popc_rate_over_peak": per_gpu * POPC_PER_PAIR / pk["popc_per_s"],
+                "algorithmic_note": "SURVEY 8d counts 8 POPC per pair; the exact prefix filter skips 6 of them for "
+                                    "> 99.9 % of the pairs, so the algorithmic rate exceeds the pipe peak -- that ratio is a "
+                                    "speed-up of the algorithm, not a roofline fraction",
+                "full_distance_variant_frac": (pairs / world / (full_ms * 1e-3)) * EXEC_POPC[0] / pk["popc_per_s"]
+                if full_ms > 0 else None}
         line["hamming"] = ham
+
+    # ------- rank 0 alone drives the GPUs from here on (in-library multi-GPU); the others wait on the host ----
+    n_dev = min(world, torch.cuda.device_count())
+    host_barrier()
+    if rank == 0 and not args.skip_hamming:
+        line["hamming"]["in_library"] = bench_group_route(torch, _lib, scanner, hashes, low_conf, HAMMING_T, n_dev,
+                                                          labels, pairs)
+        line["hamming_strong_scaling_efficiency"] = line["hamming"]["in_library"].get("strong_scaling_efficiency")
+    if rank == 0 and not args.skip_worstcase and not args.skip_hamming:
+        line["hamming"]["worst_case"] = bench_worst_case(torch, _lib, scanner, ctx, pk, args.worstcase_n)
+    if rank == 0 and not args.skip_config5:
+        line["config5"] = bench_config5(torch, _lib, scanner, ctx, args, n_dev, value, e2e_value, world)
 
     # ------------------------------------------------------------- CPU baseline (rank 0) ---
     if rank == 0 and not args.skip_cpu:
         import oracle
         oracle.build()
+        unpin_cpus()
         cores = os.cpu_count() or 1
         ns = args.cpu_sample or max(2 * cores, min(1024, Be))
         ns = min(ns, Be)
@@ -422,12 +566,187 @@ def main():
             line["hamming"]["cpu_baseline"] = {
                 "group_wall_ms": dt * 1e3, "pairs_equivalent_per_s": pairs / dt, "cores": cores, "kind": "port",
                 "sample": f"full {n} hashes, oracle MIH probing + sequential union-find (scanner.rs:1673-1807)",
-                "labels_identical": bool(np.array_equal(lab, ref_labels)), "edges_identical": bool(ref_cnt == edges)}
+                "labels_identical": bool(np.array_equal(lab, ref_labels)), "edges_identical": bool(ref_cnt == edges),
+                "in_library_labels_identical": bool(np.array_equal(line["hamming"]["in_library"]["_labels"], ref_labels))}
+    if rank == 0 and "hamming" in line:
+        line["hamming"].get("in_library", {}).pop("_labels", None)
+    host_barrier()
     if rank == 0:
         emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def pinned(torch, arr):
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t, t.numpy()
+
+
+def time_group(torch, _lib, scanner, n_dev, flags, hashes, similarity, variants=None, low_conf=None, reps=3):
+    """rh_hamming_group_multi from pinned host buffers to labels in pinned host memory, on n_dev GPUs."""
+    g = _lib.Group(n_dev=n_dev, flags=flags)
+    try:
+        out_t = torch.empty(len(hashes), dtype=torch.int32).pin_memory()
+        out = out_t.numpy().view(np.uint32)
+        scanner.group_labels_multi(g, hashes, similarity, variants=variants, low_conf=low_conf, out=out)   # warm-up
+        walls, tiles, sums = [], [], []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _, cnt = scanner.group_labels_multi(g, hashes, similarity, variants=variants, low_conf=low_conf, out=out)
+            walls.append((time.perf_counter() - t0) * 1e3)
+            t = g.last_times()
+            tiles.append(t["tile_ms_max"])
+            sums.append(t["tile_ms_sum"])
+        info = g.info()
+        return {"wall_ms": float(np.median(walls)), "tile_ms_max": float(np.median(tiles)),
+                "tile_ms_sum": float(np.median(sums)), "edges": int(cnt), "info": info, "labels": out.copy()}
+    finally:
+        g.close()
+
+
+def bench_group_route(torch, _lib, scanner, hashes, low_conf, similarity, n_dev, route_a_labels, pairs):
+    """configs[2] through ONE process and the C ABI alone: pinned host hashes -> labels in host memory on
+    1 and on n_dev GPUs; strong-scaling efficiency = t(1) / (n_dev * t(n_dev))."""
+    _, h = pinned(torch, hashes)
+    _, lc = pinned(torch, low_conf)
+    one = time_group(torch, _lib, scanner, 1, 0, h, similarity, low_conf=lc)
+    res = {"route": "one process, rh_group + rh_hamming_group_multi (in-library NCCL, tiles claimed from one pool "
+                    "over NVLink atomics); pinned host hashes in, labels in host memory out",
+           "n_gpus": n_dev, "group_wall_ms_1gpu": one["wall_ms"], "tile_kernel_ms_1gpu": one["tile_ms_max"],
+           "edges": one["edges"], "_labels": one["labels"]}
+    if n_dev > 1:
+        multi = time_group(torch, _lib, scanner, n_dev, 0, h, similarity, low_conf=lc)
+        static = time_group(torch, _lib, scanner, n_dev, _lib.GROUP_STATIC_TILES, h, similarity, low_conf=lc)
+        p2p = time_group(torch, _lib, scanner, n_dev, _lib.GROUP_NO_NCCL, h, similarity, low_conf=lc)
+        res.update({
+            "group_wall_ms": multi["wall_ms"], "tile_kernel_ms_slowest_gpu": multi["tile_ms_max"],
+            "tile_kernel_gpu_ms_sum": multi["tile_ms_sum"],
+            "pairs_per_s": pairs / (multi["wall_ms"] * 1e-3),
+            "strong_scaling_efficiency": one["wall_ms"] / (n_dev * multi["wall_ms"]),
+            "strong_scaling_efficiency_tile_kernel": one["tile_ms_max"] / (n_dev * multi["tile_ms_max"]),
+            "nccl_version": multi["info"]["nccl_version"], "work_stealing": multi["info"]["work_stealing"],
+            "labels_identical_to_1gpu": bool(np.array_equal(multi["labels"], one["labels"])),
+            "edges_identical_to_1gpu": multi["edges"] == one["edges"],
+            "static_tiles": {"group_wall_ms": static["wall_ms"], "tile_kernel_ms_slowest_gpu": static["tile_ms_max"],
+                             "labels_identical": bool(np.array_equal(static["labels"], one["labels"]))},
+            "peer_copy_exchange": {"group_wall_ms": p2p["wall_ms"],
+                                   "labels_identical": bool(np.array_equal(p2p["labels"], one["labels"]))},
+        })
+    else:
+        res.update({"group_wall_ms": one["wall_ms"], "pairs_per_s": pairs / (one["wall_ms"] * 1e-3),
+                    "strong_scaling_efficiency": 1.0})
+    if route_a_labels is not None:
+        a = route_a_labels.cpu().numpy().view(np.uint32) if torch.is_tensor(route_a_labels) else np.asarray(route_a_labels)
+        res["labels_identical_to_per_process_route"] = bool(np.array_equal(a, one["labels"]))
+    return res
+
+
+def bench_worst_case(torch, _lib, scanner, ctx, pk, n):
+    """The prefix filter's selectivity is a property of the input.  Three inputs, each searched with the
+    two-stage kernels (PF = 3, 4) and the full-distance kernel (PF = 0) at similarity 31, plus the reference's
+    default setting (similarity 40, 8 variants per file): tile-kernel time and executed-POPC fraction."""
+    from rupphash_b200.synth import planted_hashes, random_variants
+    rng = np.random.default_rng(0xADE)
+    uni, _ = planted_hashes(n, seed=0xB201, n_clusters=2000, identical_block=200, threshold=HAMMING_T)
+    adv = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    adv[:, :12] = adv[0, :12]          # every hash shares its first 96 bits: the prefix stage rejects nothing
+    sets = {"uniform_planted": torch.from_numpy(uni).cuda(),
+            "pdq_of_smooth_images": correlated_pdq_hashes(torch, ctx, n, seed=0xC0FE),
+            "adversarial_shared_96bit_prefix": torch.from_numpy(adv).cuda()}
+    pairs = n * (n - 1) // 2
+    out = {"n_hashes": n, "pairs": pairs, "similarity": HAMMING_T}
+    for name, d in sets.items():
+        row = {}
+        ref = None
+        for pf in (3, 4, 0):
+            ctx.set_option("hamming.prefilter", pf)
+            scanner.group_labels(d, HAMMING_T, ctx=ctx)
+            lab, cnt = scanner.group_labels(d, HAMMING_T, ctx=ctx)
+            ms = ctx.last_kernel_time()[0]
+            lab = lab.cpu().numpy()
+            if ref is None:
+                ref = (lab, cnt)
+            row[f"pf{pf}"] = {"tile_ms": ms, "pairs_per_s": pairs / (ms * 1e-3),
+                              "executed_popc_frac_nominal": (pairs / (ms * 1e-3)) * EXEC_POPC[pf] / pk["popc_per_s"] if pk else None,
+                              "same_result_as_pf3": bool(cnt == ref[1] and np.array_equal(lab, ref[0]))}
+        ctx.set_option("hamming.prefilter", -1)
+        row["edges"] = int(ref[1])
+        out[name] = row
+    # the reference's default: --similarity 40, 8 dihedral variants per file (README.md:13)
+    m = n // 2
+    var = torch.from_numpy(random_variants(uni[:m], seed=5)).cuda()
+    d = sets["uniform_planted"][:m].contiguous()
+    for sim in (31, 40, 63):
+        scanner.group_labels(d, sim, variants=var, ctx=ctx)
+        scanner.group_labels(d, sim, variants=var, ctx=ctx)
+        ms = ctx.last_kernel_time()[0]
+        pr = 8 * m * (m - 1) // 2
+        pf = 3 if sim <= 32 else (4 if sim <= 46 else 0)
+        out[f"variants8_similarity{sim}"] = {"n_hashes": m, "pairs": pr, "tile_ms": ms, "pairs_per_s": pr / (ms * 1e-3),
+                                             "kernel_variant": f"pf{pf}",
+                                             "executed_popc_frac": (pr / (ms * 1e-3)) * EXEC_POPC[pf] / pk["popc_per_s"] if pk else None}
+    return out
+
+
+def bench_config5(torch, _lib, scanner, ctx, args, n_dev, pdq_value, pdq_e2e_value, world):
+    """configs[4]: the 1M-file pipeline in the reference's two phases (scanner.rs:1542-1559 prints hash-phase and
+    group-phase wall time).  Hash phase: the measured PDQ rates applied to 1M images (1M distinct 1024x768 images
+    are 2.36 TB, more than HBM or host RAM hold; the pool is cycled).  Group phase: 1M files x 8 REAL dihedral
+    variants (from coefficients, scanner.rs:1615-1628) at similarity 31 and 40 (the reference's default), one
+    process driving all GPUs through the C ABI, pinned host buffers in, labels in host memory out; the CPU MIH
+    port beside it on a bounded sample of the query files."""
+    n = args.config5_n
+    d_h, d_v, d_l = dihedral_coeff_dataset(torch, ctx, n, seed=0x5EED)
+    th, h = pinned(torch, d_h.cpu().numpy())
+    tv, v = pinned(torch, d_v.cpu().numpy())
+    tl, lc = pinned(torch, d_l.cpu().numpy())
+    del d_h, d_v, d_l
+    torch.cuda.empty_cache()
+    pairs = 8 * n * (n - 1) // 2
+    out = {"n_files": n, "query_rows": 8 * n, "pairs": pairs, "n_gpus": n_dev,
+           "hash_phase": {"images": n, "device_resident_s": n / pdq_value, "pinned_host_s": n / pdq_e2e_value,
+                          "note": f"1M images at the rates measured above on {world} GPU(s) (value / e2e of this line)"},
+           "route": "one process, rh_group + rh_hamming_group_multi"}
+    cores = os.cpu_count() or 1
+    for sim in (31, 40):
+        one = time_group(torch, _lib, scanner, 1, 0, h, sim, variants=v, low_conf=lc, reps=1)
+        row = {"group_wall_ms_1gpu": one["wall_ms"], "tile_kernel_ms_1gpu": one["tile_ms_max"], "edges": one["edges"],
+               "pairs_per_s_1gpu": pairs / (one["wall_ms"] * 1e-3)}
+        lab = one["labels"]
+        row["groups"] = int((np.bincount(lab, minlength=n) > 1).sum())
+        if n_dev > 1:
+            multi = time_group(torch, _lib, scanner, n_dev, 0, h, sim, variants=v, low_conf=lc, reps=2)
+            row.update({"group_wall_ms": multi["wall_ms"], "tile_kernel_ms_slowest_gpu": multi["tile_ms_max"],
+                        "pairs_per_s": pairs / (multi["wall_ms"] * 1e-3),
+                        "strong_scaling_efficiency": one["wall_ms"] / (n_dev * multi["wall_ms"]),
+                        "labels_identical_to_1gpu": bool(np.array_equal(multi["labels"], lab)),
+                        "edges_identical_to_1gpu": multi["edges"] == one["edges"]})
+        else:
+            row.update({"group_wall_ms": one["wall_ms"], "pairs_per_s": pairs / (one["wall_ms"] * 1e-3)})
+        if not args.skip_cpu:
+            import oracle
+            oracle.build()
+            unpin_cpus()
+            # bounded sample: every stride-th 2000-file chunk of query files against the full index
+            stride = 25 if sim <= 31 else 125
+            t0 = time.perf_counter()
+            oracle.group_generic_sampled(h, sim, stride, variants=v, low_conf=lc, threads=cores)
+            dt = time.perf_counter() - t0
+            chunks = (n + 1999) // 2000
+            sampled = len(range(0, chunks, stride))
+            t1 = time.perf_counter()
+            oracle.MIHIndex(h)                       # index build alone (not scaled)
+            t_index = time.perf_counter() - t1
+            est = t_index + (dt - t_index) * chunks / sampled
+            row["cpu_baseline"] = {"estimated_group_wall_s": est, "cores": cores, "kind": "port",
+                                   "sample": f"{sampled} of {chunks} query chunks of 2000 files probed against the full MIH "
+                                             f"index ({dt:.1f} s measured, index build {t_index:.2f} s not scaled)",
+                                   "speedup_vs_cpu": est / (row["group_wall_ms"] * 1e-3)}
+        out[f"similarity{sim}"] = row
+    out["total_s_device_resident_hash_plus_group40"] = out["hash_phase"]["device_resident_s"] + \
+        out["similarity40"]["group_wall_ms"] * 1e-3
+    return out
 
 
 if __name__ == "__main__":
