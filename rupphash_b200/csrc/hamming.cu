@@ -47,7 +47,16 @@ typedef unsigned long long u64;
 struct TileMeta {
     uint32_t nc, nq;      // dense candidates / query rows
     uint32_t n_qb, n_cb;  // query blocks of HT_TQ rows, candidate blocks of HT_TC
+    uint32_t pass96, pass128;   // of PF_SAMPLES sampled (query, candidate) pairs: prefix distance <= threshold
 };
+
+// The prefix filter only pays when it rejects almost every pair: a warp refines a candidate as soon as
+// ONE of its 128 pairs survives, so at a survival rate of ~0.6 % the two-stage kernel already costs as
+// much as the full-distance one (measured: bench.py worst_case).  The rate is a property of the input
+// (uniform hashes: 2.6e-4 at threshold 31; hashes sharing a 96-bit prefix: 1), so it is sampled on the
+// device and every CTA derives the same variant from the two counters.
+constexpr uint32_t PF_SAMPLES = 16384;
+constexpr uint32_t PF_MAX_PASS = PF_SAMPLES * 3 / 1000;   // 0.3 %
 
 struct GroupArgs {
     const uint32_t *cand;     // [nc_pad][W] dense candidate hashes, zero padded to HT_TC rows
@@ -65,6 +74,7 @@ struct GroupArgs {
     u64 *next_tile;           // claim counter; claim c is tile c * claim_stride + claim_offset
     uint32_t claim_stride, claim_offset;
     int counter_is_remote;    // the counter may live in a peer GPU's memory (system-scope atomics)
+    int force_pf;             // -1: from the sampled selectivity; 0 / 3 / 4: pinned (rh_ctx_set_option)
     uint32_t nc, threshold;   // nc is filled in from meta by the kernel
 };
 
@@ -160,11 +170,66 @@ __device__ __forceinline__ uint2 claim_tile(const GroupArgs &g, const TileMeta &
 // than 1e-3 of the pairs survive; the survivors get the remaining words added and then take the
 // same exact slow path.  Results are identical to PF = 0 for any input.
 template <int PF>
+__device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_t c0, const uint32_t (&q)[HT_RQ][8],
+                                                const uint32_t (&qf)[HT_RQ], uint32_t T, const GroupArgs *s_g) {
+    uint32_t local_edges = 0;
+#pragma unroll 2
+    for (int c = 0; c < cn; c++) {
+        const uint4 a = sc[2 * c];
+        uint32_t d[HT_RQ];
+        if (PF == 0) {
+            const uint4 b = sc[2 * c + 1];
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+        } else {
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) {
+                const uint32_t x0 = q[r][0] ^ a.x, x1 = q[r][1] ^ a.y, x2 = q[r][2] ^ a.z;
+                // p(s) + 2 p(c) as one IMAD: keeps the add off the (busier) LOP3/IADD pipe
+                asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d[r]) : "r"(__popc(maj3(x0, x1, x2))), "r"(__popc(xor3(x0, x1, x2))));
+                if (PF == 4) d[r] += __popc(q[r][3] ^ a.w);
+            }
+        }
+        uint32_t mn = d[0];
+#pragma unroll
+        for (int r = 1; r < HT_RQ; r++) mn = min(mn, d[r]);
+        if (mn <= T) {
+            const uint4 b = sc[2 * c + 1];
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) {
+                if (d[r] > T) continue;
+                uint32_t full = d[r];
+                if (PF != 0) {
+                    if (PF == 3) full += __popc(q[r][3] ^ a.w);
+                    full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
+                            __popc(q[r][7] ^ b.w);
+                }
+                if (full <= T) local_edges += slow_hit(s_g, full, qf[r], c0 + c);
+            }
+        }
+    }
+    return local_edges;
+}
+
+// the variant every CTA of every GPU derives from the sampled selectivity (or the pinned one)
+__device__ __forceinline__ int choose_prefilter(const GroupArgs &g, const TileMeta &m) {
+    if (g.force_pf >= 0) return g.force_pf;
+    if (g.threshold > 63u) return 0;
+    if (m.pass96 <= PF_MAX_PASS) return 3;
+    if (m.pass128 <= PF_MAX_PASS) return 4;
+    return 0;
+}
+
+// One instantiation per variant is launched for every search; the two that the sampled selectivity
+// did not choose return at once (a few microseconds), so the variant is picked without a host round
+// trip and each instantiation keeps its own lean register allocation.
+template <int PF>
 __global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const GroupArgs g) {
     __shared__ __align__(128) uint4 s_cand[2][HT_TC * 2];
     __shared__ GroupArgs s_g;
     __shared__ TileSched s_sched;
     const TileMeta m = *g.meta;
+    if (choose_prefilter(g, m) != PF) return;
     const u64 n_tiles = g.tile_start[g.n_qb_max];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -206,6 +271,7 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const Grou
 #pragma unroll
             for (int r = 0; r < HT_RQ; r++) {
                 const uint32_t row = cur_qb * HT_TQ + r * HT_THREADS + threadIdx.x;
+                RH_CHECK_IDX(row, (size_t)m.n_qb * HT_TQ);
                 const uint4 *p = reinterpret_cast<const uint4 *>(g.qry) + (size_t)row * 2;
                 uint4 a = p[0], b = p[1];
                 q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w;
@@ -217,41 +283,7 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const Grou
         const int cn = (int)(min(c0 + (uint32_t)HT_TC, m.nc) - c0);
         rh::mbar_wait(&s_sched.bar[buf], (it >> 1) & 1u);
         const uint4 *sc = s_cand[buf];
-#pragma unroll 2
-        for (int c = 0; c < cn; c++) {
-            const uint4 a = sc[2 * c];
-            uint32_t d[HT_RQ];
-            if (PF == 0) {
-                const uint4 b = sc[2 * c + 1];
-#pragma unroll
-                for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
-            } else {
-#pragma unroll
-                for (int r = 0; r < HT_RQ; r++) {
-                    const uint32_t x0 = q[r][0] ^ a.x, x1 = q[r][1] ^ a.y, x2 = q[r][2] ^ a.z;
-                    // p(s) + 2 p(c) as one IMAD: keeps the add off the (busier) LOP3/IADD pipe
-                    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d[r]) : "r"(__popc(maj3(x0, x1, x2))), "r"(__popc(xor3(x0, x1, x2))));
-                    if (PF == 4) d[r] += __popc(q[r][3] ^ a.w);
-                }
-            }
-            uint32_t mn = d[0];
-#pragma unroll
-            for (int r = 1; r < HT_RQ; r++) mn = min(mn, d[r]);
-            if (mn <= T) {
-                const uint4 b = sc[2 * c + 1];
-#pragma unroll
-                for (int r = 0; r < HT_RQ; r++) {
-                    if (d[r] > T) continue;
-                    uint32_t full = d[r];
-                    if (PF != 0) {
-                        if (PF == 3) full += __popc(q[r][3] ^ a.w);
-                        full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
-                                __popc(q[r][7] ^ b.w);
-                    }
-                    if (full <= T) local_edges += slow_hit(&s_g, full, qf[r], c0 + c);
-                }
-            }
-        }
+        local_edges += search_tile<PF>(sc, cn, c0, q, qf, T, &s_g);
         __syncthreads();   // everyone is done with this stage; the next tile's description is visible
     }
     // one atomic per warp
@@ -336,6 +368,8 @@ __global__ void meta_kernel(const uint32_t *dpos, const uint32_t *qoff, uint32_t
     meta->nq = nq;
     meta->n_qb = (nq + HT_TQ - 1) / HT_TQ;
     meta->n_cb = (nc + HT_TC - 1) / HT_TC;
+    meta->pass96 = 0;
+    meta->pass128 = 0;
     counters[0] = 0;   // comparison_count
     counters[1] = 0;   // edges written to the optional sink
     counters[2] = 0;   // next tile to claim (unused when the group's shared counter is given)
@@ -386,6 +420,27 @@ __global__ void pad_kernel(const TileMeta *meta, uint32_t *cand, uint32_t *qry, 
     if (row < (uint32_t)HT_TC) {
         const size_t r = (size_t)m.nc + row;
         if (r < (size_t)m.n_cb * HT_TC) cand[r * W + w] = 0u;
+    }
+}
+
+// prefix-filter selectivity on PF_SAMPLES pseudo-random (query row, candidate) pairs
+__global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, TileMeta *meta, uint32_t threshold) {
+    const TileMeta m = *meta;
+    if (m.nc == 0 || m.nq == 0) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x = t * 2654435761u + 0x9E3779B9u;
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    uint32_t y = x * 0x27D4EB2Fu + 0x165667B1u;
+    y ^= y >> 15; y *= 0x2C1B3C6Du; y ^= y >> 12;
+    const uint32_t qi = x % m.nq, ci = y % m.nc;
+    const uint4 a = reinterpret_cast<const uint4 *>(qry)[(size_t)qi * 2];
+    const uint4 b = reinterpret_cast<const uint4 *>(cand)[(size_t)ci * 2];
+    const uint32_t d96 = __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z);
+    const uint32_t d128 = d96 + __popc(a.w ^ b.w);
+    const uint32_t p96 = __syncthreads_count(d96 <= threshold), p128 = __syncthreads_count(d128 <= threshold);
+    if (threadIdx.x == 0) {
+        if (p96) atomicAdd(&meta->pass96, p96);
+        if (p128) atomicAdd(&meta->pass128, p128);
     }
 }
 
@@ -544,6 +599,10 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     RH_LAUNCHED(ctx, "pad_kernel");
     iota_kernel<<<cdiv(nc_pad, 256), 256, 0, st>>>(parent, (uint32_t)nc_pad);
     RH_LAUNCHED(ctx, "iota_kernel");
+    if (W == 8) {
+        selectivity_kernel<<<PF_SAMPLES / 256, 256, 0, st>>>(cand, qry, meta, similarity);
+        RH_LAUNCHED(ctx, "selectivity_kernel");
+    }
     tile_counts_kernel<<<cdiv(n_qb_max + 1, 256), 256, 0, st>>>(qfile, meta, n_qb_max, tcount);
     RH_LAUNCHED(ctx, "tile_counts_kernel");
     tb = tmp_bytes;
@@ -574,6 +633,7 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
         g.claim_offset = (uint32_t)plan.rank;
         g.counter_is_remote = 0;
     }
+    g.force_pf = ctx->force_prefilter;
     g.nc = 0;
     g.threshold = similarity;
     out->valid = valid;
@@ -594,15 +654,12 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr, int world) {
     const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, share);
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
     if (W == 8) {
-        // two-stage search when the threshold is low enough for the prefix filter to be selective
-        int pf = pr.g.threshold <= 32 ? 3 : (pr.g.threshold <= 46 ? 4 : 0);
-        if (ctx->force_prefilter >= 0) pf = ctx->force_prefilter;   // rh_ctx_set_option (benchmarks)
-        if (pf == 3)
-            hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
-        else if (pf == 4)
-            hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
-        else
-            hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        // the variant is chosen on the device (choose_prefilter): the other two launches return at once
+        const int f = pr.g.force_pf;
+        if (f < 0 || f == 3) hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 4) hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 0) hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0) ctx->launches += 2;
     } else
         hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
     RH_LAUNCHED(ctx, "hamming_tiles_kernel");

@@ -245,6 +245,23 @@ def test_prefilter_variants_agree(ctx, orc):
         ctx.set_option("hamming.prefilter", -1)
 
 
+def test_adaptive_variant_on_unselective_prefix(ctx, orc):
+    """Hashes that share their first 96 / 128 bits defeat the prefix filter; the kernel variant is chosen on
+    the device from a sampled selectivity (full distance for such inputs) and the results stay exact."""
+    from rupphash_b200 import scanner
+    rng = np.random.default_rng(77)
+    n = 20_000
+    for shared in (12, 16):
+        hashes = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        hashes[:, :shared] = hashes[0, :shared]
+        hashes[100:140, shared:] = hashes[100, shared:]               # an identical block
+        hashes[200:230, 31] ^= np.arange(30, dtype=np.uint8)          # near duplicates
+        hashes[200:230, shared:31] = hashes[200, shared:31]
+        ref_labels, ref_cnt, _ = orc.group_generic(hashes, 31, threads=4)
+        labels, cnt = scanner.group_labels(hashes, 31, ctx=ctx)
+        assert cnt == ref_cnt and np.array_equal(labels, ref_labels), shared
+
+
 def test_group_max_dist_matches_reference_rule(ctx, orc):
     """scanner.rs:2217-2241: max over members of min over the pivot's 8 variants (or of the plain
     pivot hash when it has no coefficients)."""
