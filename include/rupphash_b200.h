@@ -100,6 +100,20 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
                       size_t row_pitch, size_t img_pitch, uint8_t *out_hash, float *out_quality,
                       float *out_coeffs, uint8_t *out_dihedral, uint8_t *out_valid);
 
+/*
+ * The same, queued: returns as soon as the copies and kernels are queued on the ctx stream.  The
+ * caller's buffers (page-locked for real overlap) must stay valid and untouched until rh_ctx_wait
+ * (ctx, *ticket) -- or rh_ctx_sync -- returns.  Calls on one ctx complete in order; up to 8 may be
+ * outstanding.  With two batches in flight the host-to-device copy of batch k+1 runs under the kernels
+ * of batch k: the scanner-style pipeline (scanner.rs:1202-1211: decode workers feed, one submitter
+ * per ctx) is the intended caller.
+ */
+int rh_pdq_hash_batch_async(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h,
+                            size_t row_pitch, size_t img_pitch, uint8_t *out_hash, float *out_quality,
+                            float *out_coeffs, uint8_t *out_dihedral, uint8_t *out_valid,
+                            uint64_t *ticket);
+int rh_ctx_wait(rh_ctx *ctx, uint64_t ticket);
+
 /* PdqFeatures::to_hash over n cached coefficient blocks (pdqhash.rs:59-61) */
 int rh_pdq_hash_from_coeffs(rh_ctx *ctx, const float *coeffs, int64_t n, uint8_t *out_hash);
 /* PdqFeatures::generate_dihedral_hashes over n blocks (pdqhash.rs:71-87; callers

@@ -24,7 +24,7 @@ PDQ_MIN_QUALITY = 50     # scanner.rs:1579
 EXPORTS = [
     "rh_ctx_create", "rh_ctx_destroy", "rh_ctx_set_stream", "rh_ctx_sync", "rh_ctx_set_option", "rh_last_error", "rh_version",
     "rh_kernel_launches", "rh_last_kernel_time", "rh_alloc_pinned", "rh_free_pinned",
-    "rh_pdq_hash_batch", "rh_pdq_hash_from_coeffs", "rh_pdq_dihedral_from_coeffs", "rh_pdq_from_buffer64",
+    "rh_pdq_hash_batch", "rh_pdq_hash_batch_async", "rh_ctx_wait", "rh_pdq_hash_from_coeffs", "rh_pdq_dihedral_from_coeffs", "rh_pdq_from_buffer64",
     "rh_phash_rotate_90", "rh_phash_rotate_180", "rh_phash_rotate_270", "rh_phash_flip_horizontal",
     "rh_phash_dihedral", "rh_phash_rotation_invariant", "rh_phash_batch",
     "rh_hamming_distances", "rh_hamming_distances_u64", "rh_hamming_group", "rh_hamming_group_shard",
@@ -81,6 +81,9 @@ def _declare(L):
     L.rh_free_pinned.argtypes = [_vp]
     L.rh_pdq_hash_batch.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                     _vp, _vp, _vp, _vp, _vp]
+    L.rh_pdq_hash_batch_async.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                          _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64)]
+    L.rh_ctx_wait.argtypes = [_vp, C.c_uint64]
     L.rh_pdq_hash_from_coeffs.argtypes = [_vp, _vp, C.c_int64, _vp]
     L.rh_pdq_dihedral_from_coeffs.argtypes = [_vp, _vp, C.c_int64, _vp]
     L.rh_pdq_from_buffer64.argtypes = [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]

@@ -41,6 +41,9 @@ struct rh_ctx {
     int pdq_prefetch_rows = 16;    // "pdq.prefetch_rows"
     int pdq_phase_clocks = 0;      // "pdq.phase_clocks": print per-phase cycle shares after each fused launch
     int pdq_variant = 0;           // "pdq.variant": 0 = default front end, other values = experiments
+    static constexpr int kTickets = 8;   // completion events of the asynchronous calls (rh_ctx_wait)
+    cudaEvent_t ev_ticket[kTickets] = {};
+    uint64_t tickets_issued = 0;
     uint64_t stage_seq = 0;        // chunks staged so far (alternates the two H2D staging buffers across calls)
 };
 

@@ -49,6 +49,8 @@ int rh_ctx_destroy(rh_ctx *ctx) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
+    for (int i = 0; i < rh_ctx::kTickets; i++)
+        if (ctx->ev_ticket[i]) cudaEventDestroy(ctx->ev_ticket[i]);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -506,11 +506,10 @@ __global__ void fill_u8_kernel(uint8_t *p, size_t n, uint8_t v) {
 
 }  // namespace
 
-extern "C" {
-
-int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h, size_t row_pitch,
-                      size_t img_pitch, uint8_t *out_hash, float *out_quality, float *out_coeffs,
-                      uint8_t *out_dihedral, uint8_t *out_valid) {
+// enqueue-only core of rh_pdq_hash_batch; `wait` = synchronise and read the kernel time before returning
+static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h, size_t row_pitch,
+                               size_t img_pitch, uint8_t *out_hash, float *out_quality, float *out_coeffs,
+                               uint8_t *out_dihedral, uint8_t *out_valid, bool wait) {
     if (!ctx) return RH_EINVAL;
     if (n < 0 || w <= 0 || h <= 0 || (n > 0 && !pixels)) return fail(ctx, RH_EINVAL, "rh_pdq_hash_batch: bad arguments");
     if (layout != RH_LAYOUT_RGB8 && layout != RH_LAYOUT_RGBA8 && layout != RH_LAYOUT_LUMA8)
@@ -545,7 +544,7 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
         RH_TRY(o_q.finish(ctx));
         RH_TRY(o_c.finish(ctx));
         RH_TRY(o_dih.finish(ctx));
-        RH_CUDA(ctx, cudaStreamSynchronize(st));
+        if (wait) RH_CUDA(ctx, cudaStreamSynchronize(st));
         return RH_OK;
     }
 
@@ -604,14 +603,17 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
         stage[1] = (uint8_t *)p;
     }
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
-    int64_t k = 0;
-    for (int64_t off = 0; off < n; off += chunk, k++) {
+    for (int64_t off = 0; off < n; off += chunk) {
         const int64_t cn = (n - off < chunk) ? (n - off) : chunk;
         const uint8_t *d_px = pixels + (size_t)off * img_pitch;
+        int b = 0;
         if (!on_device) {
-            const int b = (int)(k & 1);
-            // the staging buffer may be overwritten only once the kernels of chunk k-2 are done
-            if (k >= 2) RH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+            // the two staging buffers alternate across chunks AND across calls (asynchronous calls overlap
+            // the copy of the next batch with the kernels of this one); a buffer may be overwritten only once
+            // the kernels of the chunk staged two chunks ago are done
+            const uint64_t seq = ctx->stage_seq++;
+            b = (int)(seq & 1);
+            if (seq >= 2) RH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
             size_t bytes = (size_t)(cn - 1) * img_pitch + row_pitch * (size_t)(h - 1) + (size_t)w * ch;
             RH_CUDA(ctx, cudaMemcpyAsync(stage[b], d_px, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
             RH_CUDA(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
@@ -647,7 +649,7 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
             RH_TRY(pdq_fused_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
         else
             RH_TRY(generic_chunk(ctx, d_px, layout, down2, (int)cn, W, H, row_pitch, img_pitch, out, off, d_dct));
-        if (!on_device) RH_CUDA(ctx, cudaEventRecord(ctx->ev_done[k & 1], st));
+        if (!on_device) RH_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
     }
     RH_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
     if (o_valid.dev) {
@@ -659,11 +661,49 @@ int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n,
     RH_TRY(o_c.finish(ctx));
     RH_TRY(o_dih.finish(ctx));
     RH_TRY(o_valid.finish(ctx));
+    ctx->last_units = (double)n;
+    if (!wait) return RH_OK;
     RH_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     RH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
     ctx->last_ms = ms;
-    ctx->last_units = (double)n;
+    return RH_OK;
+}
+
+extern "C" {
+
+int rh_pdq_hash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h, size_t row_pitch,
+                      size_t img_pitch, uint8_t *out_hash, float *out_quality, float *out_coeffs,
+                      uint8_t *out_dihedral, uint8_t *out_valid) {
+    return pdq_hash_batch_impl(ctx, pixels, layout, n, w, h, row_pitch, img_pitch, out_hash, out_quality, out_coeffs,
+                               out_dihedral, out_valid, true);
+}
+
+int rh_pdq_hash_batch_async(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h, size_t row_pitch,
+                            size_t img_pitch, uint8_t *out_hash, float *out_quality, float *out_coeffs,
+                            uint8_t *out_dihedral, uint8_t *out_valid, uint64_t *ticket) {
+    int s = pdq_hash_batch_impl(ctx, pixels, layout, n, w, h, row_pitch, img_pitch, out_hash, out_quality, out_coeffs,
+                                out_dihedral, out_valid, false);
+    if (s != RH_OK) return s;
+    // completion ticket: an event after everything this call queued (results included)
+    const uint64_t t = ctx->tickets_issued++;
+    cudaEvent_t &ev = ctx->ev_ticket[t % rh_ctx::kTickets];
+    if (!ev) RH_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RH_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+    if (ticket) *ticket = t;
+    return RH_OK;
+}
+
+int rh_ctx_wait(rh_ctx *ctx, uint64_t ticket) {
+    if (!ctx) return RH_EINVAL;
+    if (ticket >= ctx->tickets_issued) return rh::fail(ctx, RH_EINVAL, "rh_ctx_wait: unknown ticket");
+    RH_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ticket + rh_ctx::kTickets < ctx->tickets_issued) {
+        // its event slot has been reused by a later call on the same stream: wait for that one instead
+        RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RH_OK;
+    }
+    RH_CUDA(ctx, cudaEventSynchronize(ctx->ev_ticket[ticket % rh_ctx::kTickets]));
     return RH_OK;
 }
 

@@ -37,6 +37,7 @@
 #include "common.cuh"
 #include "pdq_luma.cuh"
 #include "pdq_tail.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -49,7 +50,9 @@ constexpr int FBAND = 192;        // output rows per band
 constexpr int FTHREADS = 256;     // 8 warps: front end, row chains, tail
 constexpr int FMAXL = FBAND + 7;  // luma rows per band including the vertical halo (window <= 8)
 constexpr int P3_PITCH = 512;     // floats per column of the pass-3 scratch
-constexpr size_t FSMEM = (size_t)FMAXL * FLP + 16 * DCT_PITCH * 4;   // luma band (aliased by the tail) + DCT matrix
+constexpr int E_PITCH = FMAXL + 5;   // entries per edge column: index e = luma slot + 1 (e = 0: the row above the band)
+constexpr size_t FSMEM = (size_t)FMAXL * FLP + 16 * DCT_PITCH * 4 + 6 * E_PITCH * 4;   // luma band (aliased by the tail) + DCT matrix + edge columns
+static_assert(2 * (FSMEM + 1024) <= 233472, "two CTAs per SM");
 
 static_assert(sizeof(TailSmem) <= (size_t)FMAXL * FLP, "tail scratch must fit in the luma band");
 
@@ -58,22 +61,23 @@ struct FusedArgs {
     size_t row_pitch, img_pitch;
     int64_t n;
     int H;
-    const float *p2e;  // [n][H][6] pass-2 values of the six inexact columns (pdq_edge_kernel)
     float *p3t;        // [gridDim.x][64][P3_PITCH]
     const float *dct;  // 16 x 64
     TailOut out;
     int64_t out_offset;
     int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
     int pf_rows;       // plane rows between the prefetch front and the loads
+    int variant;       // A-B switches (rh_ctx_set_option "pdq.variant"): 1 = pixels without evict-first,
+                       // 2 = slab without evict-last, 4 = discard the slab's L2 lines after pass 4
     unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
 };
 
-enum { PH_FRONT = 0, PH_CHAIN, PH_P4_STAGE, PH_P4_CHAIN, PH_TAIL, NPHASE };
+enum { PH_FRONT = 0, PH_EDGE, PH_CHAIN, PH_P4_STAGE, PH_P4_CHAIN, PH_TAIL, NPHASE };
 
 // ------------------------------------------------------------------ front end ----
 
-__device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+__device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
 
 constexpr int PF_ROWS = 16;   // plane rows between the L2 prefetch front and the loads
@@ -82,15 +86,24 @@ constexpr int PF_ROWS = 16;   // plane rows between the L2 prefetch front and th
 // 3 KB source row, no registers, no shared memory.
 template <int LAYOUT, bool DOWN2>
 __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row_pitch, int H, int r0, int r1,
-                                                 int first, int step) {
+                                                 int first, int step, uint64_t pol) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr uint32_t ROWB = 8 * SPP * CH * 64;
     for (int r = max(r0, 0) + first; r < min(r1, H); r += step) {
         const uint8_t *p = base + (size_t)(r * SPP) * row_pitch;
-        l2_prefetch_row(p, ROWB);
-        if (DOWN2) l2_prefetch_row(p + row_pitch, ROWB);
+        l2_prefetch_row(p, ROWB, pol);
+        if (DOWN2) l2_prefetch_row(p + row_pitch, ROWB, pol);
     }
+}
+
+// pixels are read exactly once: 128-bit loads carry the caller's L2 policy (evict-first by default)
+template <int BYTES>
+__device__ __forceinline__ void load_px(const uint8_t *p, uint32_t *w, uint64_t pol) {
+    if (BYTES % 16 == 0)
+        load_chunk_hint<BYTES % 16 == 0 ? BYTES : 16>(p, w, pol);
+    else
+        load_chunk<BYTES>(p, w);
 }
 
 // Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep.  Each
@@ -105,7 +118,7 @@ __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row
 // pointer plus an immediate -- no pitch multiplies, no reloads of the pitch from the constant bank.
 template <int LAYOUT, bool DOWN2, bool PACKED>
 __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_t row_pitch_arg, int H, int Lr0, int nL,
-                                          uint8_t *sL, int pf_mode, int pf_rows) {
+                                          int s_begin, uint8_t *sL, int pf_mode, int pf_rows, uint64_t pol) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
@@ -114,8 +127,9 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     constexpr uint32_t ROWB = BYTES * 64;
     const size_t row_pitch = PACKED ? (size_t)ROWB : row_pitch_arg;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
-    const int s_lo = max(0, -Lr0), s_hi = min(nL, H - Lr0);
-    for (int s = rsub; s < nL; s += 4) {
+    // slots below s_begin were carried over from the previous band (rows it had already converted)
+    const int s_lo = max(s_begin, -Lr0), s_hi = min(nL, H - Lr0);
+    for (int s = s_begin + rsub; s < nL; s += 4) {
         if (s < s_lo || s >= s_hi) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + col8 * 8) = make_uint2(0u, 0u);
         if (col8 < 2) *reinterpret_cast<uint2 *>(sL + (size_t)s * FLP + FW + col8 * 8) = make_uint2(0u, 0u);
     }
@@ -128,8 +142,8 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
 #pragma unroll
     for (int q = 0; q < SETS - 1; q++) {
         if (s + 4 * q < s_hi) {
-            load_chunk<BYTES>(p + q * rstep, w0[q]);
-            if (DOWN2) load_chunk<BYTES>(p + q * rstep + row_pitch, w1[q]);
+            load_px<BYTES>(p + q * rstep, w0[q], pol);
+            if (DOWN2) load_px<BYTES>(p + q * rstep + row_pitch, w1[q], pol);
         }
     }
     while (s < s_hi) {
@@ -138,8 +152,8 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
             constexpr int AHEAD = SETS - 1;
             const int qa = (q + AHEAD) % SETS;          // the set converted AHEAD sweeps from now
             if (s + 4 * (q + AHEAD) < s_hi) {
-                load_chunk<BYTES>(p + (q + AHEAD) * rstep, w0[qa]);
-                if (DOWN2) load_chunk<BYTES>(p + (q + AHEAD) * rstep + row_pitch, w1[qa]);
+                load_px<BYTES>(p + (q + AHEAD) * rstep, w0[qa], pol);
+                if (DOWN2) load_px<BYTES>(p + (q + AHEAD) * rstep + row_pitch, w1[qa], pol);
             }
             if (q == 0 && pf_on) {
                 // PACKED rows are contiguous in memory: the 4 SETS plane rows of the sweep group pf_rows
@@ -149,7 +163,7 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
                 static_assert(PIECE % 16 == 0, "bulk prefetch granularity");
                 const int beg = ((Lr0 + f0) * SPP) * (int)ROWB + (int)(threadIdx.x >> 5) * (int)PIECE;
                 const int end = ((Lr0 + f1) * SPP) * (int)ROWB;
-                if (beg < end) l2_prefetch_row(src + beg, (uint32_t)min((int)PIECE, end - beg));
+                if (beg < end) l2_prefetch_row(src + beg, (uint32_t)min((int)PIECE, end - beg), pol);
             }
             if (s + 4 * q < s_hi) *reinterpret_cast<uint2 *>(d + 4 * q * FLP) = luma8<LAYOUT, DOWN2, NW>(w0[q], w1[q]);
         }
@@ -161,29 +175,32 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
 
 // ---------------------------------------------------------------- edge columns ----
 
-// Edge columns, step 1 (one thread per plane row, STRIDE threads): pass-1 values of the six columns
-// whose clipped row window is 5, 6 or 7 wide (box_one_d_float phases 2 and 4, pdqhash.rs:372-378,
-// :389-395) -- rounded quotients -- from the first and last 8-pixel chunk of each row, read
-// straight from global memory.  Output is column-major: sE[c * EDGE_PITCH + row].
-constexpr int EDGE_PITCH = 512 + 16;   // rows of a column + one walk batch of read-ahead, 16-byte aligned
-template <int LAYOUT, bool DOWN2, int STRIDE>
-__device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t row_pitch, int H, float *sE, int lane) {
-    constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
-    constexpr int SPP = DOWN2 ? 2 : 1;
-    constexpr int BYTES = 8 * SPP * CH;
-    constexpr int NW = BYTES / 4;
-    for (int lr = lane; lr < H; lr += STRIDE) {
-        uint32_t l0[NW], l1[DOWN2 ? NW : 1], r0[NW], r1[DOWN2 ? NW : 1];
-        const uint8_t *pl = src + (size_t)(lr * SPP) * row_pitch;
-        const uint8_t *pr = pl + (size_t)63 * BYTES;
-        load_chunk<BYTES>(pl, l0);
-        load_chunk<BYTES>(pr, r0);
-        if (DOWN2) {
-            load_chunk<BYTES>(pl + row_pitch, l1);
-            load_chunk<BYTES>(pr + row_pitch, r1);
-        }
-        const uint2 vl = luma8<LAYOUT, DOWN2, NW>(l0, l1);   // plane columns 0..7
-        const uint2 vr = luma8<LAYOUT, DOWN2, NW>(r0, r1);   // plane columns 504..511
+// The six plane columns 0,1,2,508,509,510 have clipped row windows of 5, 6 and 7 pixels, so their
+// pass-1 values are rounded quotients (box_one_d_float phases 2 and 4, pdqhash.rs:372-378, :389-395)
+// and their pass-2 values need the reference's real sequential column chain.  Both are done inside
+// the fused kernel from the luma band (no second read of the pixels):
+//   edge_inputs  one thread per luma row of the band: the six pass-1 quotients -> sE[c][slot + 1]
+//   edge_walk    six lanes, one per column: the column pass of box_one_d_float (pdqhash.rs:341-396)
+//                continued from band to band in registers, in place: on return sE[c][r - b0] is the
+//                running window sum of output row r (the row chains divide it by their row count)
+// Entry e = slot + 1 of a column belongs to plane row Lr0 + slot; entry 0 is the row above the band
+// (carried over from the previous band like the luma halo).
+// RN(s / d) for the small integer sums s <= 7 * 255 and d = 5, 6, 7 from a two-term reciprocal (the same
+// construction as div_exact below; tests/test_fused_model.py checks every (s, d) in exact arithmetic)
+__device__ __forceinline__ float div_small(int s, float yh, float yl) {
+    const float f = (float)s;
+    return __fmaf_rn(f, yh, __fmul_rn(f, yl));
+}
+
+__device__ __forceinline__ void edge_inputs(const uint8_t *sL, float *sE, int s0, int s1) {
+    // yh = RN(1/d), yl = RN(RN(1 - d yh) yh) for d = 5, 6, 7
+    const float h5 = __frcp_rn(5.0f), l5 = __fmul_rn(__fmaf_rn(-5.0f, h5, 1.0f), h5);
+    const float h6 = __frcp_rn(6.0f), l6 = __fmul_rn(__fmaf_rn(-6.0f, h6, 1.0f), h6);
+    const float h7 = __frcp_rn(7.0f), l7 = __fmul_rn(__fmaf_rn(-7.0f, h7, 1.0f), h7);
+    for (int s = s0 + (int)threadIdx.x; s < s1; s += FTHREADS) {
+        const uint8_t *row = sL + (size_t)s * FLP;
+        const uint2 vl = *reinterpret_cast<const uint2 *>(row);              // plane columns 0..7
+        const uint2 vr = *reinterpret_cast<const uint2 *>(row + FW - 8);     // plane columns 504..511
         // column 0: [0,4], column 1: [0,5], column 2: [0,6]
         const int s5 = (int)__dp4a(vl.x, 0x01010101u, 0u) + (int)(vl.y & 0xFFu);
         const int s6 = s5 + (int)((vl.y >> 8) & 0xFFu);
@@ -192,13 +209,73 @@ __device__ __forceinline__ void edge_p1(const uint8_t *__restrict__ src, size_t 
         const int t5 = (int)__dp4a(vr.y, 0x01010101u, 0u) + (int)(vr.x >> 24);
         const int t6 = t5 + (int)((vr.x >> 16) & 0xFFu);
         const int t7 = t6 + (int)((vr.x >> 8) & 0xFFu);
-        float *o = sE + lr;
-        o[0 * EDGE_PITCH] = __fdiv_rn((float)s5, 5.0f);
-        o[1 * EDGE_PITCH] = __fdiv_rn((float)s6, 6.0f);
-        o[2 * EDGE_PITCH] = __fdiv_rn((float)s7, 7.0f);
-        o[3 * EDGE_PITCH] = __fdiv_rn((float)t7, 7.0f);
-        o[4 * EDGE_PITCH] = __fdiv_rn((float)t6, 6.0f);
-        o[5 * EDGE_PITCH] = __fdiv_rn((float)t5, 5.0f);
+        float *o = sE + s + 1;
+        RH_CHECK_IDX(s + 1, E_PITCH);
+        o[0 * E_PITCH] = div_small(s5, h5, l5);
+        o[1 * E_PITCH] = div_small(s6, h6, l6);
+        o[2 * E_PITCH] = div_small(s7, h7, l7);
+        o[3 * E_PITCH] = div_small(t7, h7, l7);
+        o[4 * E_PITCH] = div_small(t6, h6, l6);
+        o[5 * E_PITCH] = div_small(t5, h5, l5);
+    }
+}
+
+// `sum` is the window sum after the last row that entered (or left) in the previous band (0 before band 0).
+template <int WC>
+__device__ __forceinline__ void edge_walk(float *col, int H, int b0, int rows_out, float &sum) {
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
+    const int Lr0 = b0 - HT;
+    const int i_first = b0 == 0 ? 0 : b0 + HB, i_last = min(b0 + rows_out - 1 + HB, H - 1);
+    // entering row i sits at e = i - Lr0 + 1, the row that leaves (i - WC) at e - WC, and the window
+    // sum of output row i - HB is written over that leaving entry (position i - HB - b0)
+    float *p = col + (i_first - Lr0 + 1);
+    int i = i_first;
+    for (; i < WC && i <= i_last; i++, p++) {      // the window is still filling (pdqhash.rs:366-378)
+        sum = __fadd_rn(sum, p[0]);
+        if (i >= HB) p[-WC] = sum;
+    }
+    // steady state (pdqhash.rs:380-387), four rows per step: the operands of the next four rows are
+    // fetched before the current four are summed, so only the add / subtract pairs sit on the chain
+    // (reading up to seven entries past the last row stays inside the column: E_PITCH leaves room)
+    float x[4], o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = p[k];
+        o[k] = p[k - WC];
+    }
+    for (; i + 3 <= i_last; i += 4, p += 4) {
+        float xn[4], on[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            xn[k] = p[4 + k];
+            on[k] = p[4 + k - WC];
+        }
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sum = __fsub_rn(__fadd_rn(sum, x[k]), o[k]);
+            r[k] = sum;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            p[k - WC] = r[k];
+            x[k] = xn[k];
+            o[k] = on[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (i + k <= i_last) {
+            sum = __fsub_rn(__fadd_rn(sum, x[k]), o[k]);
+            p[k - WC] = sum;
+        }
+    }
+    // shrink phase (pdqhash.rs:389-395): the outputs H-HB .. H-1 that belong to this band; the row that
+    // leaves for output row r sits at position r - b0, which is also where the sum goes
+    for (int r = max(H - HB, b0); r < b0 + rows_out; r++) {
+        float *q = col + (r - b0);
+        sum = __fsub_rn(sum, q[0]);
+        q[0] = sum;
     }
 }
 
@@ -244,6 +321,11 @@ __device__ __forceinline__ Recip recip2(float d) {
     return r;
 }
 
+// pass-3 samples go to the per-CTA slab in L2 and come back for pass 4: kept with evict-last priority
+__device__ __forceinline__ void st_slab(float *p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 struct ChainState {
     uint32_t aprev;   // previous even-aligned entering pair (L[e+2], L[e+3])
     uint32_t Hp;      // (H[e-2], H[e-1]): horizontal clipped 8-sums, packed u16x2
@@ -258,7 +340,7 @@ enum { G_FIRST = 0, G_MID = 1, G_LAST = 2 };
 // step.  `cur` holds luma columns 16 g .. 16 g + 15 of the lane's row.
 template <int WC, int KIND>
 __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int g, Recip y8, Recip y4,
-                                            const float *p2e, float *p3col, bool store) {
+                                            const float *pe, float cnt, float *p3col, bool store, uint64_t pol_slab) {
     const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
     for (int p = 0; p < 8; p++) {
@@ -274,16 +356,16 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
         const uint32_t b = window_sum_down<WC>(st.Hp);         // S2d of this lane's output row
         float x0, x1;
         if (KIND == G_FIRST && p == 2) {                       // e = 0, 1: inexact columns
-            x0 = p2e[0];
-            x1 = p2e[1];
+            x0 = __fdiv_rn(pe[0 * E_PITCH], cnt);     // pdqhash.rs:375, :383, :392: running sum / running count
+            x1 = __fdiv_rn(pe[1 * E_PITCH], cnt);
         } else if (KIND == G_FIRST && p == 3) {                // e = 2 inexact, e = 3 exact
-            x0 = p2e[2];
+            x0 = __fdiv_rn(pe[2 * E_PITCH], cnt);
             x1 = div_exact<true>(b, y8.h, y8.l);
         } else if (KIND == G_LAST && p == 0) {                 // e = 508, 509
-            x0 = p2e[3];
-            x1 = p2e[4];
+            x0 = __fdiv_rn(pe[3 * E_PITCH], cnt);
+            x1 = __fdiv_rn(pe[4 * E_PITCH], cnt);
         } else if (KIND == G_LAST && p == 1) {                 // e = 510 inexact; e = 511: 4-wide window
-            x0 = p2e[5];
+            x0 = __fdiv_rn(pe[5 * E_PITCH], cnt);
             x1 = div_exact<true>(b, y4.h, y4.l);
         } else {
             x0 = div_exact<false>(b, y8.h, y8.l);
@@ -298,7 +380,7 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
         if (full && (p == 2 || p == 6) && KIND != G_LAST) {
             // output column e - 4 = 8 j + 4 is decimation sample j (pdqhash.rs:439), j = (e - 8) / 8
             const int j = 2 * g - (p == 2 ? 1 : 0);
-            if (store) __stcg(p3col + (size_t)j * P3_PITCH, __fmul_rn(st.sum, 0.125f));
+            if (store) st_slab(p3col + (size_t)j * P3_PITCH, __fmul_rn(st.sum, 0.125f), pol_slab);
         }
         st.sum = __fadd_rn(st.sum, x1);
         if (full) st.sum = __fsub_rn(st.sum, st.ring[k1]);
@@ -309,8 +391,8 @@ __device__ __forceinline__ void chain_group(ChainState &st, const uint4 cur, int
 // Phase C for one band: lane = row.  Warp w owns luma slots [w OPW, w OPW + 31] of the band window
 // and produces output rows b0 + w OPW + lane for lane < OPW = 33 - WC.
 template <int WC>
-__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_img, float *p3t, int H, int b0,
-                                            int rows_out, int nL) {
+__device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, float *p3t, int H, int b0,
+                                            int rows_out, int nL, uint64_t pol_slab) {
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro = warp * OPW + lane;   // output row within the band == luma slot of the window top
@@ -320,7 +402,7 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     const float cnt = (float)max(1, hi - lo + 1);   // rows in the clipped column window
     const Recip y8 = recip2(8.0f * cnt), y4 = recip2(4.0f * cnt);
     const uint8_t *rowp = sL + (size_t)min(ro, nL - 1) * FLP;
-    const float *p2e = p2e_img + (size_t)min(r, H - 1) * 6;   // edge-column values of plane row r (pdq_edge_kernel)
+    const float *pe = sE + min(ro, rows_out - 1);   // window sums of the six edge columns for this lane's row (edge_walk)
     float *p3col = p3t + r;
     ChainState st;
     st.aprev = 0u;
@@ -333,18 +415,18 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *p2e_
     // the 16 luma bytes of group g + 1 are fetched while group g runs (no LDS latency on the chain)
     uint4 cur = *reinterpret_cast<const uint4 *>(rowp);
     uint4 nxt = *reinterpret_cast<const uint4 *>(rowp + 16);
-    chain_group<WC, G_FIRST>(st, cur, 0, y8, y4, p2e, p3col, store);
+    chain_group<WC, G_FIRST>(st, cur, 0, y8, y4, pe, cnt, p3col, store, pol_slab);
 #pragma unroll 1
     for (int g = 1; g < 32; g++) {
         cur = nxt;
         nxt = *reinterpret_cast<const uint4 *>(rowp + 16 * g + 16);   // g = 31: the zero pad at column 512
-        chain_group<WC, G_MID>(st, cur, g, y8, y4, p2e, p3col, store);
+        chain_group<WC, G_MID>(st, cur, g, y8, y4, pe, cnt, p3col, store, pol_slab);
     }
-    chain_group<WC, G_LAST>(st, nxt, 32, y8, y4, p2e, p3col, store);
+    chain_group<WC, G_LAST>(st, nxt, 32, y8, y4, pe, cnt, p3col, store, pol_slab);
     // first output of the shrink phase: column 508 = sample 63, window of 7 (pdqhash.rs:389-395).
     // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
     st.sum = __fsub_rn(st.sum, st.ring[4]);
-    if (store) __stcg(p3col + (size_t)63 * P3_PITCH, __fdiv_rn(st.sum, 7.0f));
+    if (store) st_slab(p3col + (size_t)63 * P3_PITCH, __fdiv_rn(st.sum, 7.0f), pol_slab);
 }
 
 // ------------------------------------------------------------------------ tail ----
@@ -522,13 +604,16 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     }
 }
 
+__device__ unsigned int g_front_lock[512];   // per SM (pdq.variant bit 3 experiment)
+
 template <int LAYOUT, bool DOWN2, int WC, bool PACKED>
 __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sL = smem;
     TailSmem &ts = *reinterpret_cast<TailSmem *>(smem);   // aliases the luma band, used after the last band
     float *sD = reinterpret_cast<float *>(smem + (size_t)FMAXL * FLP);   // DCT matrix, resident for the whole kernel
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, OPW = 33 - WC;
+    float *sE = sD + 16 * DCT_PITCH;                                     // the six edge columns of the current band
+    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1, OPW = 33 - WC;
     constexpr int NWC = (FBAND + OPW - 1) / OPW;           // warps that run row chains
     static_assert(NWC <= FTHREADS / 32, "one warp per OPW output rows of a band");
     const int H = a.H;
@@ -537,25 +622,55 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
     for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) sD[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
     PhaseClock clk;
     clk.start(a.phase_clk);
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    // L2 policies (a.variant bits 0 / 1 switch them off for A-B runs): streaming pixels evict-first, slab evict-last
+    const uint64_t pol_px = (a.variant & 1) ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const uint64_t pol_slab = (a.variant & 2) ? l2_policy_evict_normal() : l2_policy_evict_last();
 
     for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
         const uint8_t *src = a.px + (size_t)img * a.img_pitch;
         const uint8_t *next_src = img + gridDim.x < a.n ? src + (size_t)gridDim.x * a.img_pitch : nullptr;
+        float esum = 0.0f;   // threads 0..5: running window sum of one edge column, carried from band to band
         for (int b0 = 0; b0 < H; b0 += FBAND) {
             const int rows_out = min(FBAND, H - b0);
             const int Lr0 = b0 - HT;
             const int nL = rows_out + WC - 1;
-            front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, sL, a.pf_mode, a.pf_rows);
+            int s_begin = 0;
+            if (b0 > 0) {
+                // the band above already converted this band's first WC - 1 luma rows (its last ones): they and
+                // their edge-column entries (plus the row above them) move to the top instead of being read again
+                s_begin = WC - 1;
+                for (int idx = threadIdx.x; idx < (WC - 1) * (FLP / 16); idx += FTHREADS)
+                    reinterpret_cast<uint4 *>(sL)[idx] = reinterpret_cast<const uint4 *>(sL + (size_t)FBAND * FLP)[idx];
+                for (int idx = threadIdx.x; idx < 6 * WC; idx += FTHREADS) {
+                    const int c = idx / WC, k = idx - c * WC;
+                    sE[c * E_PITCH + k] = sE[c * E_PITCH + FBAND + k];
+                }
+                __syncthreads();
+            }
+            if (a.variant & 8) {   // experiment: the two CTAs of an SM take turns in the load phase
+                if (threadIdx.x == 0)
+                    while (atomicCAS(&g_front_lock[smid], 0u, 1u) != 0u) __nanosleep(100);
+                __syncthreads();
+            }
+            front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, s_begin, sL, a.pf_mode, a.pf_rows, pol_px);
             __syncthreads();
+            if ((a.variant & 8) && threadIdx.x == 0) atomicExch(&g_front_lock[smid], 0u);
             clk.lap(PH_FRONT);
-            if (warp < NWC) chain_phase<WC>(sL, a.p2e + (size_t)img * H * 6, p3t, H, b0, rows_out, nL);
+            edge_inputs(sL, sE, max(s_begin, -Lr0), min(nL, H - Lr0));
+            __syncthreads();
+            if (threadIdx.x < 6) edge_walk<WC>(sE + threadIdx.x * E_PITCH, H, b0, rows_out, esum);
+            __syncthreads();
+            clk.lap(PH_EDGE);
+            if (warp < NWC) chain_phase<WC>(sL, sE, p3t, H, b0, rows_out, nL, pol_slab);
             // warm L2 with the first PF_ROWS rows of whatever the front end loads next (the next band
             // of this image, else the first band of the CTA's next image), a few us before it starts
             if (lane == 0 && a.pf_mode >= 2) {
                 if (b0 + FBAND < H)
-                    l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND - HT, b0 + FBAND - HT + a.pf_rows, warp, 8);
+                    l2_prefetch_rows<LAYOUT, DOWN2>(src, a.row_pitch, H, b0 + FBAND + HB, b0 + FBAND + HB + a.pf_rows, warp, 8, pol_px);
                 else if (next_src != nullptr)
-                    l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, a.pf_rows, warp, 8);
+                    l2_prefetch_rows<LAYOUT, DOWN2>(next_src, a.row_pitch, H, 0, a.pf_rows, warp, 8, pol_px);
             }
             __syncthreads();
             clk.lap(PH_CHAIN);
@@ -564,6 +679,14 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
         __syncthreads();
         clk.lap(PH_P4_STAGE);   // (the last gather)
+        if (a.variant & 4) {
+            // the slab has been consumed: drop its (dirty) lines from L2 instead of writing them back to HBM
+            const int lines = (H * 4 + 127) / 128;
+            for (int idx = threadIdx.x; idx < 64 * lines; idx += FTHREADS) {
+                const float *q = p3t + (size_t)(idx / lines) * P3_PITCH + (idx % lines) * 32;
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(q) : "memory");
+            }
+        }
         const size_t oimg = (size_t)img + (size_t)a.out_offset;
         const float q = tail_quality(ts);
         if (threadIdx.x == 0 && a.out.quality) a.out.quality[oimg] = q;
@@ -575,56 +698,8 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
     }
 }
 
-// The six inexact columns for a whole chunk of images, one CTA of EDGE_THREADS threads per image:
-// edge_p1 over all rows (one thread per row), then the column pass of box_one_d_float (pdqhash.rs:
-// 341-396) on each of the six columns -- the same in-place walk pass 4 uses, one lane per column, plus
-// the shrink phase -- then the division by the clipped window size, results to p2e[img][row][6].
-// It reads the first and last 48 bytes of every source row (~4 % of the pixels, 32-byte sectors).
-constexpr int EDGE_THREADS = 128;
-
-template <int LAYOUT, bool DOWN2, int WC>
-__global__ void __launch_bounds__(EDGE_THREADS) pdq_edge_kernel(const uint8_t *__restrict__ px, size_t row_pitch, size_t img_pitch,
-                                                                int64_t n, int H, float *__restrict__ p2e) {
-    constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
-    __shared__ __align__(16) float sE[6 * EDGE_PITCH];
-    __shared__ float shr[6 * 4];   // the shrink-phase sums
-    const int t = threadIdx.x;
-    for (int64_t img = blockIdx.x; img < n; img += gridDim.x) {
-        edge_p1<LAYOUT, DOWN2, EDGE_THREADS>(px + (size_t)img * img_pitch, row_pitch, H, sE, t);
-        __syncthreads();
-        if (t < 6) {
-            float *col = sE + t * EDGE_PITCH;
-            float leave[HB > 0 ? HB : 1];
-#pragma unroll
-            for (int k = 0; k < HB; k++) leave[k] = col[H - WC + k];   // the walk overwrites them
-            float sum = 0.0f, prev[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-            p4_walk<WC>(col, 0, H, sum, prev);   // col[i] = window sum after row i has entered
-            sum = col[H - 1];
-#pragma unroll
-            for (int k = 0; k < HB; k++) {
-                sum = __fsub_rn(sum, leave[k]);
-                shr[t * 4 + k] = sum;
-            }
-        }
-        __syncthreads();
-        float *out = p2e + (size_t)img * H * 6;
-        for (int idx = t; idx < H * 6; idx += EDGE_THREADS) {
-            const int o = idx / 6, c = idx - 6 * o;
-            const int cnt = min(H - 1, o + HB) - max(0, o - HT) + 1;   // pdqhash.rs:375, :383, :392
-            const float v = o >= H - HB ? shr[c * 4 + (o - (H - HB))] : sE[c * EDGE_PITCH + o + HB];
-            out[idx] = __fdiv_rn(v, (float)cnt);
-        }
-        __syncthreads();
-    }
-}
-
 template <int LAYOUT, bool DOWN2, int WC>
 int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
-    pdq_edge_kernel<LAYOUT, DOWN2, WC><<<(unsigned)(a.n < 16 * 148 * 4 ? a.n : 16 * 148 * 4), EDGE_THREADS, 0, ctx->stream>>>(
-        a.px, a.row_pitch, a.img_pitch, a.n, a.H, const_cast<float *>(a.p2e));
-    RH_LAUNCHED(ctx, "pdq_edge_kernel");
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     const bool packed = a.row_pitch == (size_t)FW * (DOWN2 ? 2 : 1) * CH;
     auto kern = packed ? pdq_fused_kernel<LAYOUT, DOWN2, WC, true> : pdq_fused_kernel<LAYOUT, DOWN2, WC, false>;
@@ -668,11 +743,9 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
         return fail(ctx, RH_EINVAL, "fused PDQ kernel: pixels must be 16-byte aligned (pdq_fused_aligned)");
     int grid = ctx->sm_count * 2;
     if (grid > n) grid = (int)n;
-    void *p, *p_p3t, *p_p2e;
+    void *p, *p_p3t;
     RH_TRY(scratch(ctx, S_W3, (size_t)grid * 64 * P3_PITCH * sizeof(float), &p_p3t));
-    RH_TRY(scratch(ctx, S_W4, (size_t)n * H * 6 * sizeof(float), &p_p2e));
     FusedArgs a;
-    a.p2e = (const float *)p_p2e;
     // rh_ctx_set_option("pdq.phase_clocks", 1): per-phase cycle totals of thread 0 of every CTA, printed after the kernel
     const bool clocks = ctx->pdq_phase_clocks != 0;
     a.phase_clk = nullptr;
@@ -692,6 +765,7 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
     a.out_offset = out_offset;
     a.pf_mode = ctx->pdq_prefetch;
     a.pf_rows = ctx->pdq_prefetch_rows;
+    a.variant = ctx->pdq_variant;
     const int wc = (H + 63) / 64;
     int rc;
     if (layout == RH_LAYOUT_RGB8)
@@ -704,7 +778,7 @@ int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
         unsigned long long h[NPHASE];
         RH_CUDA(ctx, cudaMemcpyAsync(h, a.phase_clk, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        static const char *names[NPHASE] = {"front", "chain", "p4_stage", "p4_chain", "tail"};
+        static const char *names[NPHASE] = {"front", "edge", "chain", "p4_stage", "p4_chain", "tail"};
         unsigned long long tot = 0;
         for (int i = 0; i < NPHASE; i++) tot += h[i];
         fprintf(stderr, "[pdq_fused phases] n=%lld", (long long)n);

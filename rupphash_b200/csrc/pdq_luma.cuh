@@ -9,6 +9,43 @@
 
 namespace rh {
 
+// L2 eviction policies (createpolicy): pixels are read exactly once, so they are marked evict-first and
+// leave the L2 to the data that is re-read (the fused kernel's pass-3 slab).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// 128-bit read-only load with an L2 cache hint
+__device__ __forceinline__ uint4 ldg_hint(const uint4 *p, uint64_t pol) {
+    uint4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+template <int BYTES>
+__device__ __forceinline__ void load_chunk_hint(const uint8_t *p, uint32_t *w, uint64_t pol) {
+    static_assert(BYTES % 16 == 0, "hinted loads are 128-bit");
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; i++) {
+        uint4 v = ldg_hint(reinterpret_cast<const uint4 *>(p) + i, pol);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+}
+
 template <int BYTES>
 __device__ __forceinline__ void load_chunk(const uint8_t *p, uint32_t *w) {
     if (BYTES % 16 == 0) {

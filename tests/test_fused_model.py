@@ -53,6 +53,20 @@ def test_fma_division_equals_ieee_division(cnt):
             assert got == want[k], (cnt, scale, k)
 
 
+@pytest.mark.parametrize("d", [5, 6, 7])
+def test_edge_column_quotients_equal_ieee_division(d):
+    """div_small of pdq_fused.cu (pass-1 values of the six clipped columns, pdqhash.rs:372-378, :389-395):
+    every sum of up to seven u8 pixels over 5, 6 and 7, in exact rational arithmetic."""
+    dd = f32(d)
+    yh = f32(f32(1) / dd)
+    r = _rn(Fraction(1) - Fraction(float(dd)) * Fraction(float(yh)))
+    yl = _rn(Fraction(float(r)) * Fraction(float(yh)))
+    for k in range(0, 7 * 255 + 1):
+        tk = _rn(Fraction(k) * Fraction(float(yl)))
+        got = _rn(Fraction(k) * Fraction(float(yh)) + Fraction(float(tk)))
+        assert got == f32(f32(k) / dd), (d, k)
+
+
 def test_restructured_algorithm_is_bit_exact(orc):
     import fused_model
     from rupphash_b200.synth import synth_images
