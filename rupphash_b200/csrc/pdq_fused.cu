@@ -67,8 +67,9 @@ struct FusedArgs {
     int64_t out_offset;
     int pf_mode;       // L2 prefetch: 0 = off, 1 = front inside the band, 2 = + band / image starts
     int pf_rows;       // plane rows between the prefetch front and the loads
-    int variant;       // A-B switches (rh_ctx_set_option "pdq.variant"): 1 = pixels without evict-first,
-                       // 2 = slab without evict-last, 4 = discard the slab's L2 lines after pass 4
+    int variant;       // A-B switches (rh_ctx_set_option "pdq.variant"), each bit turns one default OFF:
+                       // 1 = pixels evict-first, 2 = slab evict-last, 4 = discard the slab's L2 lines after
+                       // pass 4, 8 = the two CTAs of an SM alternate in the load phase
     unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
 };
 
@@ -604,7 +605,7 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
     }
 }
 
-__device__ unsigned int g_front_lock[512];   // per SM (pdq.variant bit 3 experiment)
+__device__ unsigned int g_front_lock[512];   // one per SM: which of its two CTAs may run the load phase
 
 template <int LAYOUT, bool DOWN2, int WC, bool PACKED>
 __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs a) {
@@ -649,14 +650,17 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
                 }
                 __syncthreads();
             }
-            if (a.variant & 8) {   // experiment: the two CTAs of an SM take turns in the load phase
+            if (!(a.variant & 8)) {
+                // the two CTAs of an SM take turns in the load phase (front end ~ half of a CTA's time): one
+                // streams pixels while the other runs its chains, instead of both idling HBM or both queueing
+                // on it (+1.5-2 % measured, tools/pdq_variants.py)
                 if (threadIdx.x == 0)
                     while (atomicCAS(&g_front_lock[smid], 0u, 1u) != 0u) __nanosleep(100);
                 __syncthreads();
             }
             front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, s_begin, sL, a.pf_mode, a.pf_rows, pol_px);
             __syncthreads();
-            if ((a.variant & 8) && threadIdx.x == 0) atomicExch(&g_front_lock[smid], 0u);
+            if (!(a.variant & 8) && threadIdx.x == 0) atomicExch(&g_front_lock[smid], 0u);
             clk.lap(PH_FRONT);
             edge_inputs(sL, sE, max(s_begin, -Lr0), min(nL, H - Lr0));
             __syncthreads();
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
         __syncthreads();
         clk.lap(PH_P4_STAGE);   // (the last gather)
-        if (a.variant & 4) {
+        if (!(a.variant & 4)) {
             // the slab has been consumed: drop its (dirty) lines from L2 instead of writing them back to HBM
             const int lines = (H * 4 + 127) / 128;
             for (int idx = threadIdx.x; idx < 64 * lines; idx += FTHREADS) {

@@ -279,103 +279,276 @@ def group_max_dist(groups, hashes, pivots, coefficients=None, has_hash=None, ctx
     return out
 
 
-def hash_files_batched(images_iter, batch_size=256, want_coeffs=True, ctx=None, progress=None, depth=2, hasher=None,
-                       pinned=None):
-    """Scanner-style feeder (scanner.rs:1202-1521 restructured): decoded images of mixed sizes
-    arrive one by one (the decode stays on the host, as in the reference); same-sized images
-    are collected into batches of `batch_size`, hashed on the device, and handed back in arrival
-    order as dicts(hash, quality, quality_100, coeffs) -- or None where the reference returns
-    None (scanner.rs:1481-1487 keeps the file without a hash).
+class _PinnedPool:
+    """Every page-locked buffer the feeder allocates, so that all of them are released on every exit path."""
 
-    The reference overlaps decode and hashing with a rayon pool feeding a DbUpdate channel
-    (scanner.rs:1202-1211, :1495-1518); here the caller's iterator (the decode) runs on the calling
-    thread while ONE submitter thread owns the rh_ctx and hashes full batches, `depth` batches may be
-    queued between them, and batches are staged in recycled page-locked buffers so that the library's
-    H2D copies run at the pinned rate.  Progress ticks (scanner.rs:1206-1211) fire per finished batch as
-    progress(done, seen).  `hasher(batch_array) -> hash_batch-style dict` replaces the device (tests);
-    `pinned` defaults to True with the device hasher."""
+    def __init__(self, pinned: bool):
+        self.pinned = pinned
+        self._all = []
+
+    def empty(self, shape, dtype=np.uint8):
+        from ._lib import pinned_empty
+        if not self.pinned:
+            return np.empty(shape, dtype)
+        arr = pinned_empty(shape, dtype)
+        self._all.append(arr)
+        return arr
+
+    def close(self):
+        from ._lib import pinned_free
+        for arr in self._all:
+            pinned_free(arr)
+        self._all = []
+
+
+class _Slot:
+    """One open batch: a staging buffer of `cap` same-shaped images being filled by the decode workers."""
+    __slots__ = ("key", "buf", "cap", "idxs", "filled", "stamp")
+
+    def __init__(self, key, buf, cap):
+        self.key, self.buf, self.cap = key, buf, cap
+        self.idxs, self.filled, self.stamp = [], 0, 0
+
+
+class _DeviceHasher:
+    """rh_pdq_hash_batch_async with results in recycled page-locked arrays: submit() queues a batch and
+    returns at once, wait() blocks until that batch's results are in host memory."""
+
+    def __init__(self, ctx, want_coeffs, pool, max_images):
+        self.ctx, self.want_coeffs, self.pool, self.max_images = ctx, want_coeffs, pool, max_images
+        self.free = []
+
+    def _outs(self):
+        if self.free:
+            return self.free.pop()
+        m = self.max_images
+        return {"hash": self.pool.empty((m, 32)), "quality": self.pool.empty((m,), np.float32),
+                "valid": self.pool.empty((m,)),
+                "coeffs": self.pool.empty((m, 256), np.float32) if self.want_coeffs else None}
+
+    def submit(self, arr):
+        n, h, w = arr.shape[0], arr.shape[1], arr.shape[2]
+        o = self._outs()
+        ticket = C.c_uint64()
+        self.ctx.check(lib().rh_pdq_hash_batch_async(
+            self.ctx.handle, ptr(arr), pdqhash._layout_of(arr.shape[1:]), n, w, h, 0, 0, ptr(o["hash"]), ptr(o["quality"]),
+            ptr(o["coeffs"]), None, ptr(o["valid"]), C.byref(ticket)))
+        return ticket.value, o, n
+
+    def wait(self, handle):
+        ticket, o, n = handle
+        self.ctx.check(lib().rh_ctx_wait(self.ctx.handle, ticket))
+        res = {k: (None if v is None else v[:n].copy()) for k, v in o.items()}
+        self.free.append(o)
+        return res
+
+
+def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progress=None, depth=2, hasher=None,
+                       pinned=None, decode=None, workers=0, batch_bytes=256 << 20, max_open_shapes=8, inflight=2):
+    """Scanner-style feeder (scanner.rs:1202-1521 restructured): files are decoded on the host (as in the
+    reference), same-sized images are collected into batches, hashed on the device, and handed back in
+    arrival order as dicts(hash, quality, quality_100, coeffs) -- or None where the reference returns None
+    (scanner.rs:1481-1487 keeps the file without a hash).
+
+    items    an iterable.  With decode=None it yields decoded images and is consumed on the calling thread.
+             With `decode` (item -> HxW[xC] uint8 array or None) and `workers` > 0 a pool of decode threads
+             pulls items and decodes them in parallel -- the reference's rayon pool (scanner.rs:1188-1205) --
+             and copies each image straight into a slot of the page-locked staging batch of its shape.
+    batches  at most `batch_size` images AND at most `batch_bytes` of pixels each (large photos get small
+             batches), at most `max_open_shapes` partly filled batches at a time (the least recently used one
+             is sent early), staging buffers are recycled, and every page-locked buffer is released on exit.
+    device   ONE submitter thread owns the rh_ctx; it keeps `inflight` batches queued with
+             rh_pdq_hash_batch_async so that the copy of batch k+1 runs under the kernels of batch k.
+    progress ticks (scanner.rs:1206-1211) fire per finished batch as progress(done, seen).
+    `hasher(batch_array) -> hash_batch-style dict` replaces the device (CPU tests); `pinned` defaults to True
+    with the device."""
     import queue
     import threading
-    from ._lib import pinned_empty, pinned_free
-    if hasher is None:
+    device = hasher is None
+    if device:
         ctx = ctx or default_context()
-        hasher = lambda arr: pdqhash.hash_batch(arr, want_coeffs=want_coeffs, ctx=ctx)   # noqa: E731
         pinned = True if pinned is None else pinned
-    pinned = bool(pinned)
-    results = {}
+    pool = _PinnedPool(bool(pinned))
+    results, failure = {}, []
     seen = [0]
-    lock = threading.Lock()
+    lock = threading.Condition()
     work = queue.Queue(maxsize=max(1, depth))
-    free_bufs = {}            # nbytes -> [arrays]: recycled staging buffers
-    failure = []
+    free_bufs = {}            # (cap, shape) -> [staging arrays]
+    open_slots = {}           # shape -> _Slot
+    stamp = [0]
 
-    def take_buffer(shape):
-        nbytes = int(np.prod(shape))
+    def publish(idxs, out):
+        valid, quality, hashes = np.asarray(out["valid"]), np.asarray(out["quality"]), np.asarray(out["hash"])
+        coeffs = None if out.get("coeffs") is None else np.asarray(out["coeffs"])
         with lock:
-            pool = free_bufs.get(nbytes)
-            if pool:
-                return pool.pop().reshape(shape)
-        return pinned_empty(shape, np.uint8) if pinned else np.empty(shape, np.uint8)
+            for k, i in enumerate(idxs):
+                if not valid[k]:
+                    results[i] = None
+                    continue
+                q = float(quality[k])
+                results[i] = {"hash": hashes[k].copy(), "quality": q, "quality_100": quality_100(q),
+                              "coeffs": coeffs[k].copy() if coeffs is not None else None}
+            done, total = len(results), seen[0]
+        if progress:
+            progress(done, total)
+
+    def recycle(slot):
+        with lock:
+            free_bufs.setdefault((slot.cap, slot.key), []).append(slot.buf)
 
     def submitter():
-        while True:
-            item = work.get()
-            if item is None:
-                return
-            idxs, buf = item
-            if failure:
-                continue      # drain the queue after an error so that the producer never blocks
-            try:
-                out = hasher(buf[: len(idxs)])
-                valid, quality, hashes = np.asarray(out["valid"]), np.asarray(out["quality"]), np.asarray(out["hash"])
-                coeffs = None if out.get("coeffs") is None else np.asarray(out["coeffs"])
-                with lock:
-                    for k, i in enumerate(idxs):
-                        if not valid[k]:
-                            results[i] = None
-                            continue
-                        q = float(quality[k])
-                        results[i] = {"hash": hashes[k].copy(), "quality": q, "quality_100": quality_100(q),
-                                      "coeffs": coeffs[k].copy() if coeffs is not None else None}
-                    free_bufs.setdefault(buf.size, []).append(buf.reshape(-1))
-                    done, total = len(results), seen[0]
-                if progress:
-                    progress(done, total)
-            except BaseException as e:   # handed to the caller
-                failure.append(e)
+        dev = None
+        pending = []          # queued device batches, oldest first
+        try:
+            while True:
+                item = work.get()
+                if item is None:
+                    break
+                if failure:
+                    continue      # drain the queue after an error so that the producers never block
+                slot = item
+                arr = slot.buf[: len(slot.idxs)]
+                if device:
+                    if dev is None:
+                        cap = max(1, min(batch_size, 1 << 16))
+                        dev = _DeviceHasher(ctx, want_coeffs, pool, cap)
+                    pending.append((dev.submit(arr), slot))
+                    if len(pending) >= max(1, inflight):
+                        h, s = pending.pop(0)
+                        publish(s.idxs, dev.wait(h))
+                        recycle(s)
+                else:
+                    publish(slot.idxs, hasher(arr))
+                    recycle(slot)
+            while pending and not failure:
+                h, s = pending.pop(0)
+                publish(s.idxs, dev.wait(h))
+                recycle(s)
+        except BaseException as e:   # handed to the caller
+            failure.append(e)
+            while True:               # keep draining until the sentinel so that producers never block
+                try:
+                    if work.get(timeout=0.05) is None:
+                        break
+                except queue.Empty:
+                    if done_feeding[0]:
+                        break
+        finally:
+            if device and pending:
+                try:
+                    ctx.sync()
+                except Exception:
+                    pass
+
+    done_feeding = [False]
+
+    def send(slot):
+        """slot has left open_slots: wait for the copies in progress, then queue it"""
+        with lock:
+            while slot.filled < len(slot.idxs):
+                lock.wait()
+        if slot.idxs:
+            work.put(slot)
+
+    def stage(i, img):
+        """copy one decoded image into the open batch of its shape; full / evicted batches go to the submitter"""
+        if img is None:
+            with lock:
+                results[i] = None
+            return
+        img = np.asarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        if w < pdqhash.MIN_HASHABLE_DIM or h < pdqhash.MIN_HASHABLE_DIM:
+            with lock:
+                results[i] = None
+            return
+        key = img.shape
+        evicted = None
+        with lock:
+            slot = open_slots.get(key)
+            if slot is None:
+                if len(open_slots) >= max(1, max_open_shapes):      # send the least recently used batch early
+                    lru = min(open_slots.values(), key=lambda s: s.stamp)
+                    evicted = open_slots.pop(lru.key)
+                cap = int(max(1, min(batch_size, batch_bytes // max(1, img.nbytes))))
+                bufs = free_bufs.get((cap, key))
+                buf = bufs.pop() if bufs else None
+                slot = open_slots[key] = _Slot(key, buf, cap)
+            k = len(slot.idxs)
+            slot.idxs.append(i)
+            stamp[0] += 1
+            slot.stamp = stamp[0]
+            full = len(slot.idxs) >= slot.cap
+            if full:
+                del open_slots[key]
+            creator = slot.buf is None and k == 0
+        if creator:                                                 # a (blocking) page-locked allocation: not under the lock
+            buf = pool.empty((slot.cap,) + key, np.uint8)
+            with lock:
+                slot.buf = buf
+                lock.notify_all()
+        else:
+            with lock:
+                while slot.buf is None:
+                    lock.wait()
+        slot.buf[k] = img                                           # the copy into the staging buffer
+        with lock:
+            slot.filled += 1
+            lock.notify_all()
+        if evicted is not None:
+            send(evicted)
+        if full:
+            send(slot)
 
     th = threading.Thread(target=submitter, name="rh-submitter", daemon=True)
     th.start()
-    pending = {}              # image shape -> (indices, staging buffer)
+    decoders = []
     try:
-        for i, img in enumerate(images_iter):
-            if failure:
-                break
-            with lock:
-                seen[0] = i + 1
-            img = np.asarray(img, dtype=np.uint8)
-            h, w = img.shape[:2]
-            if w < pdqhash.MIN_HASHABLE_DIM or h < pdqhash.MIN_HASHABLE_DIM:
+        if decode is not None and workers and workers > 0:
+            it = iter(items)
+            it_lock = threading.Lock()
+
+            def decoder():
+                while not failure:
+                    with it_lock:
+                        try:
+                            item = next(it)
+                        except StopIteration:
+                            return
+                        except BaseException as e:
+                            failure.append(e)
+                            return
+                        with lock:
+                            i = seen[0]
+                            seen[0] = i + 1
+                    try:
+                        stage(i, decode(item))
+                    except BaseException as e:
+                        failure.append(e)
+                        return
+            decoders = [threading.Thread(target=decoder, name=f"rh-decode-{k}", daemon=True) for k in range(int(workers))]
+            for d in decoders:
+                d.start()
+            for d in decoders:
+                d.join()
+        else:
+            for i, item in enumerate(items):
+                if failure:
+                    break
                 with lock:
-                    results[i] = None
-                continue
-            key = img.shape
-            slot = pending.get(key)
-            if slot is None:
-                slot = pending[key] = ([], take_buffer((batch_size,) + key))
-            slot[1][len(slot[0])] = img          # the copy into the staging buffer
-            slot[0].append(i)
-            if len(slot[0]) >= batch_size:
-                work.put(pending.pop(key))
-        for key in list(pending):
-            work.put(pending.pop(key))
+                    seen[0] = i + 1
+                stage(i, decode(item) if decode is not None else item)
+        if not failure:
+            with lock:
+                rest = sorted(open_slots.values(), key=lambda s: s.stamp)
+                open_slots.clear()
+            for slot in rest:
+                send(slot)
     finally:
+        done_feeding[0] = True
         work.put(None)
         th.join()
-        if pinned:
-            for pool in free_bufs.values():
-                for b in pool:
-                    pinned_free(b)
+        pool.close()
     if failure:
         raise failure[0]
     return [results[i] for i in range(seen[0])]

@@ -73,3 +73,51 @@ def test_decode_and_hashing_overlap():
     wall = time.perf_counter() - t0
     serial = n * t_decode + (n // bs) * t_hash
     assert len(res) == n and wall < 0.8 * serial, (wall, serial)
+
+
+def test_batches_are_bounded_by_bytes():
+    """a batch never stages more than batch_bytes of pixels, whatever batch_size says."""
+    calls = []
+    shapes = [(100, 100, 3)] * 7
+    res = scanner.hash_files_batched(images(shapes), batch_size=256, batch_bytes=70_000, hasher=fake_hasher(calls))
+    assert [r["hash"][0] for r in res] == list(range(7))
+    assert sorted(c[0][0] for c in calls) == [1, 2, 2, 2]          # 30 kB images: two per batch
+
+
+def test_open_shape_slots_are_capped():
+    """Many camera resolutions: at most max_open_shapes partly filled batches exist, the least recently used
+    one is hashed early; nothing is lost or reordered."""
+    shapes = [(8 + (k % 5), 8, 3) for k in range(40)]
+    calls = []
+    res = scanner.hash_files_batched(images(shapes), batch_size=64, max_open_shapes=2, hasher=fake_hasher(calls))
+    assert [r["hash"][0] for r in res] == list(range(40))
+    assert len(calls) > 5                                           # evictions produced early, partial batches
+    assert sum(c[0][0] for c in calls) == 40
+
+
+def test_decode_workers_fill_batches_in_parallel():
+    """A pool of decode threads (the reference's rayon pool, scanner.rs:1188-1205) pulls file names, decodes and
+    stages; results still come back in arrival order and decoding overlaps itself."""
+    n, t_decode = 48, 0.02
+    names = []
+
+    def decode(k):
+        names.append(threading.current_thread().name)
+        time.sleep(t_decode)
+        return None if k == 7 else np.full((8, 8, 3), k, np.uint8)
+    t0 = time.perf_counter()
+    res = scanner.hash_files_batched(range(n), decode=decode, workers=8, batch_size=4, hasher=fake_hasher([]))
+    wall = time.perf_counter() - t0
+    assert res[7] is None and res[13] is None
+    assert [r["hash"][0] for k, r in enumerate(res) if r is not None] == [k for k in range(n) if k not in (7, 13)]
+    assert len(set(names)) > 1 and all(nm.startswith("rh-decode-") for nm in names)
+    assert wall < 0.5 * n * t_decode, wall
+
+
+def test_decode_error_reaches_the_caller():
+    def decode(k):
+        if k == 5:
+            raise OSError("unreadable file")
+        return np.full((8, 8, 3), k, np.uint8)
+    with pytest.raises(OSError, match="unreadable"):
+        scanner.hash_files_batched(range(20), decode=decode, workers=3, batch_size=4, hasher=fake_hasher([]))
