@@ -20,6 +20,9 @@
 namespace rh {
 int pdq_fused_supported(int W, int H);
 int pdq_fused_aligned(const void *px, size_t row_pitch, size_t img_pitch);
+int pdq_float_supported(int W, int H);
+int pdq_float_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int64_t n, int W, int H, size_t row_pitch,
+                  size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct);
 int pdq_fused_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int64_t n, int W, int H, size_t row_pitch,
                   size_t img_pitch, const TailOut &out, int64_t out_offset, const float *d_dct);
 }  // namespace rh
@@ -573,13 +576,18 @@ static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, i
     const bool fused = pdq_fused_supported(W, H) != 0 && !ctx->pdq_force_generic &&
                        (resize ? (((size_t)W * H) & 15) == 0
                                : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
+    // every other plane up to 512 x 512 whose width is a multiple of 8 (portrait photos, small images): the
+    // float-chain fused kernel; what remains (odd widths, tiny planes, unaligned rows) takes the generic pipeline
+    const bool fused_float = !fused && pdq_float_supported(W, H) != 0 && !ctx->pdq_force_generic &&
+                             (resize ? (((size_t)W * H) & 15) == 0
+                                     : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
     // (device-resident input to the fused kernel needs 9 KB of scratch per image: one launch for up
     // to 16384 images, so that the persistent CTAs see a long queue)
     // (the generic pipeline keeps ~10 B of scratch per plane pixel; 1024 images give its one-warp-per-32-columns
     // walks enough warps to hide their load latency)
-    int64_t chunk = fused ? (on_device ? 16384 : 2048) : 1024;
+    int64_t chunk = (fused || fused_float) ? (on_device ? 16384 : 2048) : 1024;
     if (resize) {   // full-resolution luma + the horizontally resized plane live in scratch
         int64_t c3 = (int64_t)((size_t(1) << 30) / ((size_t)w * h + (size_t)W * h + (size_t)W * H));
         if (c3 < 1) c3 = 1;
@@ -643,10 +651,14 @@ static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, i
             RH_LAUNCHED(ctx, "box_resize_kernel");
             if (fused)
                 RH_TRY(pdq_fused_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+            else if (fused_float)
+                RH_TRY(pdq_float_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
             else
                 RH_TRY(generic_chunk(ctx, Lr, RH_LAYOUT_LUMA8, false, (int)cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
         } else if (fused)
             RH_TRY(pdq_fused_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
+        else if (fused_float)
+            RH_TRY(pdq_float_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
         else
             RH_TRY(generic_chunk(ctx, d_px, layout, down2, (int)cn, W, H, row_pitch, img_pitch, out, off, d_dct));
         if (!on_device) RH_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));

@@ -35,8 +35,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "pdq_luma.cuh"
-#include "pdq_tail.cuh"
+#include "pdq_pass4.cuh"
 #include "tma.cuh"
 
 namespace {
@@ -47,14 +46,12 @@ constexpr int FW = 512;           // plane width served by this kernel
 constexpr int FLP = 528;          // luma row pitch in bytes: 512 + 16 zero bytes; 528 % 128 == 16
                                   // keeps the per-row LDS.128 of 8 consecutive lanes conflict-free
 constexpr int FBAND = 192;        // output rows per band
-constexpr int FTHREADS = 256;     // 8 warps: front end, row chains, tail
 constexpr int FMAXL = FBAND + 7;  // luma rows per band including the vertical halo (window <= 8)
-constexpr int P3_PITCH = 512;     // floats per column of the pass-3 scratch
 constexpr int E_PITCH = FMAXL + 5;   // entries per edge column: index e = luma slot + 1 (e = 0: the row above the band)
 constexpr size_t FSMEM = (size_t)FMAXL * FLP + 16 * DCT_PITCH * 4 + 6 * E_PITCH * 4;   // luma band (aliased by the tail) + DCT matrix + edge columns
 static_assert(2 * (FSMEM + 1024) <= 233472, "two CTAs per SM");
 
-static_assert(sizeof(TailSmem) <= (size_t)FMAXL * FLP, "tail scratch must fit in the luma band");
+static_assert(P4_SMEM_BYTES <= (size_t)FMAXL * FLP, "tail scratch + pass-4 staging must fit in the luma band");
 
 struct FusedArgs {
     const uint8_t *px;
@@ -73,7 +70,6 @@ struct FusedArgs {
     unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
 };
 
-enum { PH_FRONT = 0, PH_EDGE, PH_CHAIN, PH_P4_STAGE, PH_P4_CHAIN, PH_TAIL, NPHASE };
 
 // ------------------------------------------------------------------ front end ----
 
@@ -96,15 +92,6 @@ __device__ __forceinline__ void l2_prefetch_rows(const uint8_t *base, size_t row
         l2_prefetch_row(p, ROWB, pol);
         if (DOWN2) l2_prefetch_row(p + row_pitch, ROWB, pol);
     }
-}
-
-// pixels are read exactly once: 128-bit loads carry the caller's L2 policy (evict-first by default)
-template <int BYTES>
-__device__ __forceinline__ void load_px(const uint8_t *p, uint32_t *w, uint64_t pol) {
-    if (BYTES % 16 == 0)
-        load_chunk_hint<BYTES % 16 == 0 ? BYTES : 16>(p, w, pol);
-    else
-        load_chunk<BYTES>(p, w);
 }
 
 // Phase F: fill the luma band.  64 threads per plane row (8 pixels each), 4 rows per sweep.  Each
@@ -322,11 +309,6 @@ __device__ __forceinline__ Recip recip2(float d) {
     return r;
 }
 
-// pass-3 samples go to the per-CTA slab in L2 and come back for pass 4: kept with evict-last priority
-__device__ __forceinline__ void st_slab(float *p, float v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
-}
-
 struct ChainState {
     uint32_t aprev;   // previous even-aligned entering pair (L[e+2], L[e+3])
     uint32_t Hp;      // (H[e-2], H[e-1]): horizontal clipped 8-sums, packed u16x2
@@ -428,181 +410,6 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
     // P2[504] entered at g = 31, p = 6 and sits in ring[(2*6) & 7].
     st.sum = __fsub_rn(st.sum, st.ring[4]);
     if (store) st_slab(p3col + (size_t)63 * P3_PITCH, __fdiv_rn(st.sum, 7.0f), pol_slab);
-}
-
-// ------------------------------------------------------------------------ tail ----
-
-// Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
-// columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
-// memory P4_ROWS rows at a time with cp.async (16 bytes per request, no registers, every request of a
-// chunk in flight at once) into two buffers: chunk c + 1 lands while threads 0..63 (one per column)
-// walk chunk c at shared-memory latency, so only the first chunk's L2 round trip is exposed.
-// The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit accesses of the walk (8 lanes
-// per wavefront) are conflict-free.
-constexpr int P4_ROWS = 128;
-constexpr int P4_PITCH = P4_ROWS + 4;
-static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitch");
-static_assert((64 * (P4_ROWS / 4)) % FTHREADS == 0 && P4_ROWS % 8 == 0, "pass-4 staging has no remainder");
-constexpr size_t P4_STAGE_OFF = (sizeof(TailSmem) + 15) & ~size_t(15);   // 16-byte aligned for the 128-bit accesses
-static_assert(P4_STAGE_OFF + 2 * 64 * P4_PITCH * 4 <= (size_t)FMAXL * FLP, "pass-4 staging must fit beside the tail scratch");
-
-__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct PhaseClock {
-    unsigned long long *acc;
-    long long t;
-    __device__ __forceinline__ void start(unsigned long long *p) {
-        acc = p;
-        if (acc != nullptr && threadIdx.x == 0) t = clock64();
-    }
-    // call right after the barrier that ends phase `ph`
-    __device__ __forceinline__ void lap(int ph) {
-        if (acc != nullptr && threadIdx.x == 0) {
-            const long long now = clock64();
-            atomicAdd(acc + ph, (unsigned long long)(now - t));
-            t = now;
-        }
-    }
-};
-
-// Running window sums of pass 4 for one staged chunk, in place: on return colp[i] holds the window
-// sum after plane row c0 + i has entered (= the sum of output row c0 + i - HB).  Nothing but the
-// dependent add / subtract pair per row sits on the chain: decimation and the division by the row
-// count are done afterwards by the whole CTA (p4_gather).
-template <int WC>
-__device__ __forceinline__ void p4_walk(float *colp, int c0, int rows, float &sum, float (&prev)[8]) {
-    float cur[8];
-    int r0 = 0;
-    if (c0 == 0) {   // rows 0 .. 7: the window is still filling for ri < WC (pdqhash.rs:366-378)
-        const float4 lo = *reinterpret_cast<const float4 *>(colp);
-        const float4 hi = *reinterpret_cast<const float4 *>(colp + 4);
-        cur[0] = lo.x; cur[1] = lo.y; cur[2] = lo.z; cur[3] = lo.w;
-        cur[4] = hi.x; cur[5] = hi.y; cur[6] = hi.z; cur[7] = hi.w;
-        float sums[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            sum = __fadd_rn(sum, cur[k]);
-            if (k >= WC) sum = __fsub_rn(sum, cur[k - WC]);
-            sums[k] = sum;
-        }
-        *reinterpret_cast<float4 *>(colp) = make_float4(sums[0], sums[1], sums[2], sums[3]);
-        *reinterpret_cast<float4 *>(colp + 4) = make_float4(sums[4], sums[5], sums[6], sums[7]);
-#pragma unroll
-        for (int k = 0; k < 8; k++) prev[k] = cur[k];
-        r0 = 8;
-    }
-    // steady state (pdqhash.rs:380-387); rows past the image in the last batch are computed on
-    // whatever the staging left there and never read
-    // (the next batch is loaded before the current one is summed: no LDS latency between batches; the
-    // read one batch past the chunk stays inside the staging area)
-    float4 lo = *reinterpret_cast<const float4 *>(colp + r0);
-    float4 hi = *reinterpret_cast<const float4 *>(colp + r0 + 4);
-#pragma unroll 1
-    for (; r0 < rows; r0 += 8) {
-        cur[0] = lo.x; cur[1] = lo.y; cur[2] = lo.z; cur[3] = lo.w;
-        cur[4] = hi.x; cur[5] = hi.y; cur[6] = hi.z; cur[7] = hi.w;
-        lo = *reinterpret_cast<const float4 *>(colp + r0 + 8);
-        hi = *reinterpret_cast<const float4 *>(colp + r0 + 12);
-        float sums[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float old = (k >= WC) ? cur[k - WC] : prev[8 + k - WC];
-            sum = __fsub_rn(__fadd_rn(sum, cur[k]), old);
-            sums[k] = sum;
-        }
-        *reinterpret_cast<float4 *>(colp + r0) = make_float4(sums[0], sums[1], sums[2], sums[3]);
-        *reinterpret_cast<float4 *>(colp + r0 + 4) = make_float4(sums[4], sums[5], sums[6], sums[7]);
-#pragma unroll
-        for (int k = 0; k < 8; k++) prev[k] = cur[k];
-    }
-}
-
-// Decimated rows whose window sum lies in the staged chunk (or in the shrink-phase sums `shr`, for the
-// last HB output rows) -> B, divided by the number of rows in the clipped window (pdqhash.rs:372,
-// :385, :393: the reference divides the running sum by its running count).
-template <int WC>
-__device__ __forceinline__ void p4_gather(const float *stage, const float *shr, int H, int c0, int rows, bool last, float *B) {
-    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1, HT = WC - HALF;
-    const int j = threadIdx.x & 63;
-    // first output whose window sum can lie in this chunk: o + HB >= c0  <=  (2 i + 1) H >= 128 (c0 - HB)
-    const int i_lo = max(0, (128 * (c0 - HB) - H) / (2 * H));
-    for (int i = i_lo + (threadIdx.x >> 6); i < 64; i += FTHREADS / 64) {
-        const int o = ((2 * i + 1) * H) >> 7;   // decimated output row (pdqhash.rs:435)
-        if (!last && o + HB - c0 >= rows) break;   // the rest belongs to later chunks
-        const int src = o + HB - c0;            // staged slot whose sum is output row o
-        const float cnt = (float)(min(o + HB, H - 1) - max(o - HT, 0) + 1);
-        if (o >= H - HB) {
-            if (last) B[i * 64 + j] = __fdiv_rn(shr[(o - (H - HB)) * 64 + j], cnt);
-        } else if (src >= 0 && src < rows) {
-            B[i * 64 + j] = __fdiv_rn(stage[j * P4_PITCH + src], cnt);
-        }
-    }
-}
-
-// plane rows [c0, c0 + P4_ROWS) of the 64 columns -> stg (rows past H are copied but never used;
-// the clamp keeps the last chunk inside its column)
-__device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg) {
-#pragma unroll 1
-    for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
-        const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
-        cp_async16(stg + col * P4_PITCH + 4 * q, p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4));
-    }
-    cp_async_commit();
-}
-
-template <int WC>
-__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, PhaseClock &clk) {
-    constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
-    const int j = threadIdx.x;
-    float sum = 0.0f;
-    float prev[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-    p4_issue(p3t, 0, stage);
-    if (P4_ROWS < H) p4_issue(p3t, P4_ROWS, stage + 64 * P4_PITCH);
-    int buf = 0;
-    for (int c0 = 0; c0 < H; c0 += P4_ROWS, buf ^= 1) {
-        float *stg = stage + buf * (64 * P4_PITCH);
-        const int rows = min(P4_ROWS, H - c0);
-        const bool last = c0 + P4_ROWS >= H;
-        // the rows that leave during the shrink phase (H-WC .. H-WC+HB-1), fetched under the walk
-        float leave[HB > 0 ? HB : 1];
-        if (last && j < 64) {
-#pragma unroll
-            for (int k = 0; k < HB; k++) leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
-        }
-        if (last)
-            cp_async_wait<0>();
-        else
-            cp_async_wait<1>();   // everything but the chunk after this one has landed
-        __syncthreads();
-        clk.lap(PH_P4_STAGE);
-        if (j < 64) {
-            p4_walk<WC>(stg + j * P4_PITCH, c0, rows, sum, prev);
-            if (last) {   // shrink phase (pdqhash.rs:389-395): outputs H-HB .. H-1
-                // the walk may have run past row H-1 inside its last batch of 8: restart from the sum of row H-1
-                sum = stg[j * P4_PITCH + rows - 1];
-#pragma unroll
-                for (int k = 0; k < HB; k++) {
-                    sum = __fsub_rn(sum, leave[k]);
-                    shr[k * 64 + j] = sum;
-                }
-            }
-        }
-        __syncthreads();
-        clk.lap(PH_P4_CHAIN);
-        p4_gather<WC>(stg, shr, H, c0, rows, last, B);
-        if (c0 + 2 * P4_ROWS < H) {   // this buffer takes the chunk after the next one
-            __syncthreads();
-            p4_issue(p3t, c0 + 2 * P4_ROWS, stg);
-        }
-    }
 }
 
 __device__ unsigned int g_front_lock[512];   // one per SM: which of its two CTAs may run the load phase

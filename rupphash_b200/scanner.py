@@ -552,3 +552,271 @@ def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progre
     if failure:
         raise failure[0]
     return [results[i] for i in range(seen[0])]
+
+
+# ------------------------------------------------------------------ group post-processing ----
+# scanner.rs:1986-2022 process_raw_groups, :2183-2254 analyze_group_with_features, :2040-2110 sort_files,
+# :2256-2262 sort_by_stem_then_ext, :1561-1576 the final group order.  Path and metadata logic runs on the
+# host (it is string work); the one data-parallel piece, max_dist over every group, is a single
+# rh_group_max_dist call for the whole library.
+
+RAW_EXTS = ("nef", "dng", "cr2", "cr3", "arw", "orf", "rw2", "raf", "kdc", "dcr", "pef", "x3f", "srf", "3fr")  # scanner.rs:43-46
+STATUS_NONE, STATUS_SOME_IDENTICAL, STATUS_ALL_IDENTICAL = "None", "SomeIdentical", "AllIdentical"
+
+
+class FileMeta:
+    """The fields of FileMetadata (scanner.rs to_file_metadata) that grouping output depends on."""
+    __slots__ = ("path", "size", "modified", "content_hash", "pixel_hash", "pdqhash", "exif_timestamp", "index")
+
+    def __init__(self, path, size=0, modified=0, content_hash=b"", pixel_hash=None, pdqhash=None, exif_timestamp=None,
+                 index=None):
+        self.path, self.size, self.modified = path, size, modified
+        self.content_hash, self.pixel_hash, self.pdqhash = content_hash, pixel_hash, pdqhash
+        self.exif_timestamp, self.index = exif_timestamp, index
+
+
+def _file_name(path: str) -> str:
+    import os
+    return os.path.basename(path)
+
+
+def _file_stem(path: str) -> str:
+    import os
+    return os.path.splitext(os.path.basename(path))[0]
+
+
+def is_raw_ext(path: str) -> bool:
+    """scanner.rs:2264-2269"""
+    import os
+    ext = os.path.splitext(os.path.basename(path))[1]
+    return ext[1:].lower() in RAW_EXTS if ext else False
+
+
+def natural_key(s: str):
+    """Sort key with the order of natord::compare (Martin Pool's strnatcmp, case-sensitive, whitespace
+    skipped): digit runs compare as numbers -- right-aligned (longer run is larger, then the first differing
+    digit) unless one of them starts with '0', in which case they compare left-aligned like fractions.
+    The `natord` crate is not in the reference tree; this restates its published algorithm."""
+    import functools
+
+    def cmp(a: str, b: str) -> int:
+        ai = bi = 0
+        na, nb = len(a), len(b)
+        while True:
+            while ai < na and a[ai].isspace():
+                ai += 1
+            while bi < nb and b[bi].isspace():
+                bi += 1
+            ca = a[ai] if ai < na else ""
+            cb = b[bi] if bi < nb else ""
+            if ca.isdigit() and cb.isdigit():
+                if ca == "0" or cb == "0":        # left-aligned ("fractional") comparison
+                    while True:
+                        da = a[ai] if ai < na else ""
+                        db = b[bi] if bi < nb else ""
+                        if not da.isdigit() and not db.isdigit():
+                            r = 0
+                            break
+                        if not da.isdigit():
+                            return -1
+                        if not db.isdigit():
+                            return 1
+                        if da != db:
+                            return -1 if da < db else 1
+                        ai += 1
+                        bi += 1
+                else:                              # right-aligned: the longer run wins, else the first difference
+                    bias = 0
+                    while True:
+                        da = a[ai] if ai < na else ""
+                        db = b[bi] if bi < nb else ""
+                        if not da.isdigit() and not db.isdigit():
+                            r = bias
+                            break
+                        if not da.isdigit():
+                            return -1
+                        if not db.isdigit():
+                            return 1
+                        if bias == 0 and da != db:
+                            bias = -1 if da < db else 1
+                        ai += 1
+                        bi += 1
+                if r:
+                    return r
+                continue
+            if not ca and not cb:
+                return 0
+            if ca != cb:
+                return -1 if ca < cb else 1
+            ai += 1
+            bi += 1
+    return functools.cmp_to_key(cmp)(s)
+
+
+def sort_files(files: list, sort_order: str) -> None:
+    """scanner.rs:2040-2110, in place; every branch is a stable sort as in the reference ("random" and
+    "location" leave the order alone: the reference shuffles / defers to the GUI)."""
+    name = lambda f: _file_name(f.path)                    # noqa: E731
+    nat = lambda f: natural_key(_file_name(f.path))        # noqa: E731
+    if sort_order == "name":
+        files.sort(key=name)
+    elif sort_order == "name-desc":
+        files.sort(key=name)
+        files.reverse()
+    elif sort_order == "name-natural":
+        files.sort(key=nat)
+    elif sort_order == "name-natural-desc":
+        files.sort(key=nat)
+        files.reverse()
+    elif sort_order == "date":
+        files.sort(key=lambda f: f.modified)
+    elif sort_order == "date-desc":
+        files.sort(key=lambda f: f.modified, reverse=True)   # sort_by_key(Reverse(..)): stable, ties keep their order
+    elif sort_order == "size":
+        files.sort(key=lambda f: f.size)
+    elif sort_order == "size-desc":
+        files.sort(key=lambda f: f.size, reverse=True)
+    elif sort_order in ("exif-date", "exif-date-desc"):
+        sign = 1 if sort_order == "exif-date" else -1
+        files.sort(key=lambda f: (0, sign * f.exif_timestamp) if f.exif_timestamp is not None else (1, sign * f.modified))
+    elif sort_order in ("random", "location"):
+        pass
+    else:
+        files.sort(key=nat)
+
+
+def sort_by_stem_then_ext(files: list) -> None:
+    """scanner.rs:2256-2262: same stem together, the RAW file after its JPEG."""
+    files.sort(key=lambda f: (_file_stem(f.path), is_raw_ext(f.path)))
+
+
+def _arrange_group(files: list, sort_order: str):
+    """The ordering half of analyze_group_with_features (scanner.rs:2189-2212) -> (files, status)."""
+    counts = {}
+    for f in files:
+        counts[f.content_hash] = counts.get(f.content_hash, 0) + 1
+    duplicates = [f for f in files if counts[f.content_hash] > 1]
+    unique = [f for f in files if counts[f.content_hash] <= 1]
+    duplicates.sort(key=lambda f: ((0, b"") if f.pixel_hash is None else (1, bytes(f.pixel_hash)), bytes(f.content_hash),
+                                   _file_name(f.path)))
+    sort_files(unique, sort_order)
+    out = duplicates + unique
+    sort_by_stem_then_ext(out)
+    if len(counts) == 1:
+        status = STATUS_ALL_IDENTICAL
+    elif any(c > 1 for c in counts.values()):
+        status = STATUS_SOME_IDENTICAL
+    else:
+        status = STATUS_NONE
+    return out, status
+
+
+def process_raw_groups(raw_groups, files, sort_order="name-natural", coefficients=None, ctx=None, max_dist_fn=None,
+                       dihedral_fn=None):
+    """scanner.rs:1986-2022 -> (groups of FileMeta in display order, infos [{max_dist, status}]).
+
+    raw_groups: index lists (the output of group_files_generic / merge_groups_by_stem); files: FileMeta per
+    scanned file; coefficients: {file index: 256 f32} for the files that carry cached PDQ features
+    (features_map, scanner.rs:1995-2000).  Every group is ordered like analyze_group_with_features does, its
+    pivot is the first file with features (8 dihedral variants) or else the first file with a hash
+    (scanner.rs:2217-2241), and max_dist of ALL groups comes from one rh_group_max_dist call.
+    `max_dist_fn(pivot_variants, n_variants, member_hashes, member_group, n_groups)` and `dihedral_fn(coeffs)`
+    replace the device calls (CPU tests of the host logic); the product path never sets them."""
+    coefficients = coefficients or {}
+    groups, statuses = [], []
+    for idxs in raw_groups:
+        members = []
+        for i in idxs:
+            f = files[i]
+            if f.index is None:
+                f.index = i
+            members.append(f)
+        arranged, status = _arrange_group(members, sort_order.lower())
+        groups.append(arranged)
+        statuses.append(status)
+    ng = len(groups)
+    piv = np.zeros((ng, 8, 32), np.uint8)
+    nv = np.ones(ng, np.uint8)
+    feat_groups, feat_coeffs = [], []
+    mem_h, mem_g = [], []
+    for g, arranged in enumerate(groups):
+        with_feat = next((f for f in arranged if f.index in coefficients), None)
+        if with_feat is not None:
+            feat_groups.append(g)
+            feat_coeffs.append(np.asarray(coefficients[with_feat.index], np.float32).reshape(256))
+        else:
+            with_hash = next((f for f in arranged if f.pdqhash is not None), None)
+            if with_hash is not None:
+                piv[g, 0] = np.frombuffer(bytes(with_hash.pdqhash), np.uint8)
+            else:
+                nv[g] = 0                     # no pivot: max_dist 0 (scanner.rs:2239-2241)
+        for f in arranged:
+            if f.pdqhash is not None:
+                mem_h.append(np.frombuffer(bytes(f.pdqhash), np.uint8))
+                mem_g.append(g)
+    if feat_groups:
+        if dihedral_fn is not None:
+            var = dihedral_fn(np.stack(feat_coeffs))
+        else:
+            ctx = ctx or default_context()
+            var = pdqhash.dihedral_from_coeffs(np.stack(feat_coeffs), ctx)
+        piv[np.asarray(feat_groups)] = np.asarray(var)
+        nv[np.asarray(feat_groups)] = 8
+    mem_h = np.stack(mem_h) if mem_h else np.zeros((0, 32), np.uint8)
+    mem_g = np.asarray(mem_g, np.uint32)
+    # groups without a pivot take no part in the reduce
+    keep = nv[mem_g] > 0 if len(mem_g) else np.zeros(0, bool)
+    mem_h, mem_g = np.ascontiguousarray(mem_h[keep]), np.ascontiguousarray(mem_g[keep])
+    nv_call = np.maximum(nv, 1).astype(np.uint8)
+    if ng == 0:
+        max_dist = np.zeros(0, np.uint32)
+    elif max_dist_fn is not None:
+        max_dist = np.asarray(max_dist_fn(piv, nv_call, mem_h, mem_g, ng), np.uint32)
+    else:
+        ctx = ctx or default_context()
+        max_dist = np.zeros(ng, np.uint32)
+        ctx.check(lib().rh_group_max_dist(ctx.handle, ptr(piv), ptr(nv_call), ptr(mem_h), ptr(mem_g), len(mem_g), ng,
+                                          ptr(max_dist)))
+    infos = [{"max_dist": int(max_dist[g]) if nv[g] else 0, "status": statuses[g]} for g in range(ng)]
+    return groups, infos
+
+
+def sort_groups(groups, infos):
+    """The final order of scan_and_group (scanner.rs:1561-1576): groups with identical files first, then
+    by max_dist ascending, then by the size of the first file descending (stable)."""
+    order = sorted(range(len(groups)), key=lambda g: (0 if infos[g]["status"] != STATUS_NONE else 1, infos[g]["max_dist"],
+                                                       -(groups[g][0].size if groups[g] else 0)))
+    return [groups[g] for g in order], [infos[g] for g in order]
+
+
+def scan_groups(files, similarity, sort_order="name-natural", coefficients=None, quality100=None, ctx=None):
+    """The grouping half of scan_and_group (scanner.rs:1542-1576) on already hashed files: edge phase +
+    union-find on the device, stem merge, per-group ordering, max_dist, final group order -- the list
+    `phdupes` prints.  files: FileMeta per scanned file (pdqhash None = not hashed)."""
+    ctx = ctx or default_context()
+    n = len(files)
+    hashes = np.zeros((n, 32), np.uint8)
+    has_hash = np.zeros(n, np.uint8)
+    for i, f in enumerate(files):
+        f.index = i
+        if f.pdqhash is not None:
+            hashes[i] = np.frombuffer(bytes(f.pdqhash), np.uint8)
+            has_hash[i] = 1
+    coefficients = coefficients or {}
+    variants = np.zeros((n, 8, 32), np.uint8)
+    variants[:, 0] = hashes
+    n_variants = np.ones(n, np.uint8)
+    idx = [i for i in sorted(coefficients) if has_hash[i]]
+    if idx:
+        variants[np.asarray(idx)] = pdqhash.dihedral_from_coeffs(
+            np.stack([np.asarray(coefficients[i], np.float32).reshape(256) for i in idx]), ctx)
+        n_variants[np.asarray(idx)] = 8
+    low_conf = None
+    if quality100 is not None:
+        low_conf = np.array([1 if is_low_confidence(q) else 0 for q in quality100], np.uint8)
+    raw, comparisons = group_files_generic(hashes, similarity, has_hash=has_hash, variants=variants, n_variants=n_variants,
+                                           low_conf=low_conf, ctx=ctx)
+    raw = merge_groups_by_stem(raw, [f.path for f in files])
+    groups, infos = process_raw_groups(raw, files, sort_order, coefficients, ctx)
+    groups, infos = sort_groups(groups, infos)
+    return groups, infos, comparisons

@@ -67,6 +67,20 @@ def test_edge_column_quotients_equal_ieee_division(d):
         assert got == f32(f32(k) / dd), (d, k)
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_pass1_quotients_of_the_float_kernel(d):
+    """pass1_pair of pdq_float.cu: window sums of up to eight u8 pixels over the clipped window size 1..8,
+    by the same two-term reciprocal, in exact rational arithmetic."""
+    dd = f32(d)
+    yh = f32(f32(1) / dd)
+    r = _rn(Fraction(1) - Fraction(float(dd)) * Fraction(float(yh)))
+    yl = _rn(Fraction(float(r)) * Fraction(float(yh)))
+    for k in range(0, 8 * 255 + 1):
+        tk = _rn(Fraction(k) * Fraction(float(yl)))
+        got = _rn(Fraction(k) * Fraction(float(yh)) + Fraction(float(tk)))
+        assert got == f32(f32(k) / dd), (d, k)
+
+
 def test_restructured_algorithm_is_bit_exact(orc):
     import fused_model
     from rupphash_b200.synth import synth_images

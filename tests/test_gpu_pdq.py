@@ -99,7 +99,11 @@ def test_hash_and_dihedral_from_coeffs(ctx, orc):
                                    # column windows 4, 5, 7 of the fused kernel (16:9, 2:1, 8:7 ... shapes)
                                    (576, 1024, 3), (288, 512, 3), (448, 512, 3), (896, 1024, 4), (400, 512),
                                    (250, 512, 3), (193, 512, 3), (256, 512, 4), (257, 512, 3), (320, 512),
-                                   (386, 512, 3), (512, 1024, 3), (640, 1024), (192, 512, 3)])
+                                   (386, 512, 3), (512, 1024, 3), (640, 1024), (192, 512, 3),
+                                   # the float-chain fused kernel (pdq_float.cu): portrait and small planes, row windows 2..8
+                                   (1024, 768, 3), (512, 384, 3), (512, 384), (1024, 768, 4), (512, 256, 3),
+                                   (400, 320, 3), (128, 72, 3), (65, 512, 3), (100, 128), (512, 504, 4),
+                                   (333, 200, 3), (1024, 640), (72, 80, 3), (511, 440, 3), (129, 136)])
 def test_hash_batch_bit_exact(ctx, orc, shape):
     from rupphash_b200 import pdqhash
     h, w = shape[:2]
@@ -145,6 +149,7 @@ def test_too_small_is_none(ctx):
 
 
 @pytest.mark.parametrize("shape", [(854, 1280, 3), (720, 1080, 3), (768, 780, 3), (1280, 854, 3), (513, 513),
+                                   (1200, 900, 3), (2000, 1500), (700, 525, 4),
                                    (600, 2000, 4), (1537, 640, 3), (5, 4000, 3)])
 def test_general_box_predownsample(ctx, orc, shape):
     """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
