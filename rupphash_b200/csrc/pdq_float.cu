@@ -67,15 +67,17 @@ __device__ __forceinline__ float div_count(float sum, int cnt) {
 
 // Phase F for luma rows [i0, i1) of the plane: W / 8 threads per row, 8 plane pixels each, two register
 // sets (the loads of the next row are in flight while this one is converted).
+// `tid` in [0, nthreads): the first band is converted by the whole CTA, the others by warps 1..7 while warp 0
+// runs the previous band's row chains.
 template <int LAYOUT, bool DOWN2>
-__device__ __forceinline__ void front_rows(const uint8_t *__restrict__ src, size_t row_pitch, int W8, int i0, int i1,
-                                           uint8_t *sL, uint64_t pol) {
+__device__ __noinline__ void front_rows(const uint8_t *__restrict__ src, size_t row_pitch, int W8, int i0, int i1,
+                                           uint8_t *sL, uint64_t pol, int tid, int nthreads) {
     constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;
     constexpr int NW = BYTES / 4;
-    const int per_sweep = FTHREADS / W8;             // rows converted per sweep
-    const int rsub = (int)threadIdx.x / W8, col8 = (int)threadIdx.x - rsub * W8;
+    const int per_sweep = nthreads / W8;             // rows converted per sweep
+    const int rsub = tid / W8, col8 = tid - rsub * W8;
     if (rsub >= per_sweep) return;
     uint32_t w0[2][NW], w1[2][DOWN2 ? NW : 1];
     const size_t rstep = (size_t)per_sweep * SPP * row_pitch;
@@ -149,59 +151,80 @@ __device__ __forceinline__ float2 pass1_pair(const uint8_t *row, const ColumnSet
     return make_float2(__fmaf_rn(f0, cs.y0h, __fmul_rn(f0, cs.y0l)), __fmaf_rn(f1, cs.y1h, __fmul_rn(f1, cs.y1l)));
 }
 
+// A decimated sample of the row chain: divide by the clipped window size and store.  Out of line on purpose:
+// inlined, the compiler evaluates the (IEEE) division speculatively for EVERY column of the chain.
+__device__ __noinline__ void emit_sample(float sum, int o, int W, int ht, int hb, float *dst, uint64_t pol_slab) {
+    st_slab(dst, div_count(sum, window_count(o, W, ht, hb)), pol_slab);
+}
+
 // Phase P3 for one row of the pass-2 band (one lane): the row pass of box_one_d_float (pdqhash.rs:341-396)
 // over W samples with window wr, keeping the 64 decimated columns floor((2 j + 1) W / 128) (pdqhash.rs:439).
-__device__ __forceinline__ void row_chain(const float *q, int W, int wr, float *slab_row, uint64_t pol_slab) {
+__device__ __noinline__ void row_chain(const float *q, int W, int wr, float *slab_row, uint64_t pol_slab) {
+    // (out of line: the chain gets its own register allocation instead of competing with the whole kernel)
     const int half = (wr + 2) / 2, ht = wr - half, hb = half - 1;
     float sum = 0.0f;
     int j = 0, target = W >> 7;   // next decimated column
-    auto emit = [&](int o) {
-        if (o == target) {
-            st_slab(slab_row + (size_t)j * P3_PITCH, div_count(sum, window_count(o, W, ht, hb)), pol_slab);
-            j++;
-            target = ((2 * j + 1) * W) >> 7;
-        }
-    };
     int i = 0;
     for (; i < wr; i++) {            // the window fills (pdqhash.rs:366-378)
         sum = __fadd_rn(sum, q[i]);
-        if (i >= hb) emit(i - hb);
-    }
-    // steady state (pdqhash.rs:380-387), four columns per step with the operands fetched ahead
-    float x[4], o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        x[k] = q[i + k];
-        o[k] = q[i + k - wr];
-    }
-    for (; i + 3 < W; i += 4) {
-        float xn[4], on[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {   // (reads up to 7 floats past the row: inside the band buffer)
-            xn[k] = q[i + 4 + k];
-            on[k] = q[i + 4 + k - wr];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            sum = __fsub_rn(__fadd_rn(sum, x[k]), o[k]);
-            emit(i + k - hb);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            x[k] = xn[k];
-            o[k] = on[k];
+        if (i - hb == target) {
+            emit_sample(sum, i - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
+            j++;
+            target = ((2 * j + 1) * W) >> 7;
         }
     }
+    // steady state (pdqhash.rs:380-387), four columns per step with the operands fetched ahead;
+    // `t` counts down to the next decimated column so that the test is one compare per column
+    const float *pe = q + i, *pl = q + i - wr;   // entering / leaving samples
+    float x0 = pe[0], x1 = pe[1], x2 = pe[2], x3 = pe[3];
+    float o0 = pl[0], o1 = pl[1], o2 = pl[2], o3 = pl[3];
+    int t = target - (i - hb);      // columns until the next sample (0 = this one)
+    for (; i + 3 < W; i += 4, pe += 4, pl += 4) {
+        // (reads up to 7 floats past the row: inside the band buffer)
+        const float n0 = pe[4], n1 = pe[5], n2 = pe[6], n3 = pe[7];
+        const float m0 = pl[4], m1 = pl[5], m2 = pl[6], m3 = pl[7];
+        const float s0 = __fsub_rn(__fadd_rn(sum, x0), o0);
+        const float s1 = __fsub_rn(__fadd_rn(s0, x1), o1);
+        const float s2 = __fsub_rn(__fadd_rn(s1, x2), o2);
+        const float s3 = __fsub_rn(__fadd_rn(s2, x3), o3);
+        sum = s3;
+        if (t < 4) {                 // a decimated column among these four (they are >= 1.1 columns apart: at most 4)
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        if (i + k < W) {
-            sum = __fsub_rn(__fadd_rn(sum, x[k]), o[k]);
-            emit(i + k - hb);
+            for (int k = 0; k < 4; k++) {
+                if (t == k) {
+                    const float sk = k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3));
+                    emit_sample(sk, i + k - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
+                    j++;
+                    target = ((2 * j + 1) * W) >> 7;
+                    t = target - (i - hb);
+                }
+            }
+        }
+        t -= 4;
+        x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+        o0 = m0; o1 = m1; o2 = m2; o3 = m3;
+    }
+    {
+        const float xs[3] = {x0, x1, x2}, os[3] = {o0, o1, o2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (i + k < W) {
+                sum = __fsub_rn(__fadd_rn(sum, xs[k]), os[k]);
+                if (i + k - hb == target) {
+                    emit_sample(sum, i + k - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
+                    j++;
+                    target = ((2 * j + 1) * W) >> 7;
+                }
+            }
         }
     }
     for (int oo = W - hb; oo < W; oo++) {   // shrink phase (pdqhash.rs:389-395)
         sum = __fsub_rn(sum, q[oo - ht - 1]);
-        emit(oo);
+        if (oo == target) {
+            emit_sample(sum, oo, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
+            j++;
+            target = ((2 * j + 1) * W) >> 7;
+        }
     }
 }
 
@@ -239,12 +262,34 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
                 reinterpret_cast<uint32_t *>(row + 16 + W)[k - 4] = 0u;
         }
         float sum0 = 0.0f, sum1 = 0.0f;   // pass-2 running sums of the thread's two columns
+        constexpr bool WC_POW2 = (WC & (WC - 1)) == 0;
+        front_rows<LAYOUT, DOWN2>(src, a.row_pitch, W8, 0, min(GBR, H), sL, pol_px, (int)threadIdx.x, FTHREADS);
+        __syncthreads();
+        clk.lap(PH_FRONT);
         for (int i0 = 0; i0 < H; i0 += GBR) {
             const int i1 = min(i0 + GBR, H);
             const bool last = i1 == H;
-            front_rows<LAYOUT, DOWN2>(src, a.row_pitch, W8, i0, i1, sL, pol_px);
-            __syncthreads();
-            clk.lap(PH_FRONT);
+            // pull the source rows of the next band (or of the first band of the CTA's next image) into L2
+            // while this band's columns are computed: one bulk prefetch per source row
+            {
+                constexpr int CH = LAYOUT == RH_LAYOUT_RGB8 ? 3 : (LAYOUT == RH_LAYOUT_RGBA8 ? 4 : 1);
+                constexpr int SPP = DOWN2 ? 2 : 1;
+                const uint32_t row_bytes = ((uint32_t)(W * SPP * CH)) & ~15u;
+                const uint8_t *base = nullptr;
+                int rows = 0;
+                if (!last) {
+                    base = src + (size_t)(i1 * SPP) * a.row_pitch;
+                    rows = (min(i1 + GBR, H) - i1) * SPP;
+                } else if (img + gridDim.x < a.n) {
+                    base = src + (size_t)gridDim.x * a.img_pitch;
+                    rows = min(GBR, H) * SPP;
+                }
+                if (base != nullptr && (int)threadIdx.x < rows && row_bytes)
+                    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(
+                                     base + (size_t)threadIdx.x * a.row_pitch),
+                                 "r"(row_bytes), "l"(pol_px)
+                                 : "memory");
+            }
             const int r0 = max(0, i0 - HB);                       // first pass-2 row this band produces
             const int nb = (last ? H : i1 - HB) - r0;             // and how many
             if (active) {
@@ -260,11 +305,17 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
                     }
                     *ring = x;
                     if (i >= HB) {
-                        const int o = i - HB, cnt = window_count(o, H, HT, HB);
+                        const int o = i - HB;
                         float *dst = sP2 + (size_t)(o - r0) * P2P + c0;
                         RH_CHECK_IDX(o - r0, GP2_ROWS);
-                        dst[0] = div_count(sum0, cnt);
-                        dst[1] = div_count(sum1, cnt);
+                        if (i >= WC - 1) {                        // the full window (every row but the first few)
+                            dst[0] = WC_POW2 ? __fmul_rn(sum0, 1.0f / WC) : __fdiv_rn(sum0, (float)WC);
+                            dst[1] = WC_POW2 ? __fmul_rn(sum1, 1.0f / WC) : __fdiv_rn(sum1, (float)WC);
+                        } else {
+                            const int cnt = window_count(o, H, HT, HB);
+                            dst[0] = div_count(sum0, cnt);
+                            dst[1] = div_count(sum1, cnt);
+                        }
                     }
                 }
                 if (last) {
@@ -282,12 +333,18 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
             }
             __syncthreads();
             clk.lap(PH_EDGE);    // (reported as "p12")
-            for (int base = 32 * warp; base < nb; base += FTHREADS) {
-                const int lr = base + lane;
-                if (lr < nb) row_chain(sP2 + (size_t)lr * P2P, W, wr, p3t + r0 + lr, pol_slab);
+            // warp 0: the row chains of this band; warps 1..7: the luma rows of the next band
+            if (warp == 0) {
+                for (int base = 0; base < nb; base += 32) {
+                    const int lr = base + lane;
+                    if (lr < nb) row_chain(sP2 + (size_t)lr * P2P, W, wr, p3t + r0 + lr, pol_slab);
+                }
+            } else if (!last) {
+                front_rows<LAYOUT, DOWN2>(src, a.row_pitch, W8, i1, min(i1 + GBR, H), sL, pol_px, (int)threadIdx.x - 32,
+                                          FTHREADS - 32);
             }
             __syncthreads();
-            clk.lap(PH_CHAIN);
+            clk.lap(PH_CHAIN);   // ("p3 + next front")
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
