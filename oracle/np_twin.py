@@ -36,6 +36,48 @@ def downsample_2x(luma: np.ndarray) -> np.ndarray:
     return ((hz[0::2, :] + hz[1::2, :] + 1) >> 1).astype(np.uint8)
 
 
+def box_weight_matrix(in_size: int, out_size: int):
+    """fast_image_resize 6.1.0 `Convolution(FilterType::Box)` coefficients for one axis, written independently of
+    oracle_pdq.c's sparse (xmin, count, taps) loops: a DENSE (out, in) matrix built by broadcasting.
+    Pillow-derived rule: scale = in/out (>= 1 when shrinking), support = scale / 2, an input pixel x belongs to
+    output o when its centre x + 0.5 lies in (centre - support, centre + support] with centre = (o + 0.5) scale,
+    restricted to the integer span [floor(centre - support + 0.5), floor(centre + support + 0.5)); equal weights,
+    normalised per output; fixed point at the largest precision that keeps every coefficient below 2^15.
+    The crate is not in the reference tree: parity with it is unpinned.  -> (int matrix, precision)"""
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 0.5 * fscale
+    o = np.arange(out_size, dtype=np.float64)[:, None]
+    x = np.arange(in_size, dtype=np.float64)[None, :]
+    centre = (o + 0.5) * scale
+    lo = np.maximum(np.floor(centre - support + 0.5), 0.0)
+    hi = np.minimum(np.floor(centre + support + 0.5), float(in_size))
+    t = (x - centre + 0.5) / fscale
+    member = (x >= lo) & (x < hi) & (t > -0.5) & (t <= 0.5)
+    wgt = member.astype(np.float64)
+    tot = wgt.sum(axis=1, keepdims=True)
+    wgt = np.divide(wgt, tot, out=np.zeros_like(wgt), where=tot != 0)
+    biggest = float(wgt.max())
+    precision = 0
+    while precision < 22 and int(0.5 + biggest * float(1 << (precision + 1))) < (1 << 15):
+        precision += 1
+    scaled = wgt * float(1 << precision)
+    k = np.where(scaled < 0, np.ceil(scaled - 0.5), np.floor(scaled + 0.5)).astype(np.int64)
+    return k, precision
+
+
+def resize_box_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """pdqhash.rs:203-220 (resize_luma_fast): horizontal pass into a u8 plane, then vertical; each pass is
+    (sum(px * k) + 2^(p-1)) >> p clipped to [0, 255]."""
+    sh, sw = src.shape
+    kx, px = box_weight_matrix(sw, dw)
+    ky, py = box_weight_matrix(sh, dh)
+    a = src.astype(np.int64)
+    hz = np.clip((a @ kx.T + (1 << (px - 1))) >> px, 0, 255)            # (sh, dw)
+    out = np.clip((ky @ hz + (1 << (py - 1))) >> py, 0, 255)            # (dh, dw)
+    return out.astype(np.uint8)
+
+
 def box_lines(x: np.ndarray, win: int) -> np.ndarray:
     """pdqhash.rs:341-396 applied along axis 1 of a (lines, len) float32 array."""
     lines, n = x.shape
@@ -173,14 +215,12 @@ def pdq_from_luma(luma: np.ndarray, d: np.ndarray):
 
 
 def pdq_features(img: np.ndarray, d: np.ndarray):
-    """pdqhash.rs:166-196 for RGB8 / Luma8 arrays whose pre-downsample is absent or exactly 2x"""
+    """pdqhash.rs:166-196 for RGB8 / RGBA8 / Luma8 arrays"""
     h, w = img.shape[:2]
     if w < 5 or h < 5:
         return None
     luma = img if img.ndim == 2 else luma601(img)
     if w > 512 or h > 512:
         nw, nh = target_dimensions(w, h)
-        if (nw * 2, nh * 2) != (w, h):
-            raise NotImplementedError("numpy twin only covers the exact-2x pre-downsample")
-        luma = downsample_2x(luma)
+        luma = downsample_2x(luma) if (nw * 2, nh * 2) == (w, h) else resize_box_u8(luma, nw, nh)
     return pdq_from_luma(luma, d)

@@ -231,8 +231,9 @@ inline GroupResult group_files_generic(const Context &c, const std::vector<pdqha
 }
 
 
-// group_files_generic::<u64> with PHashStrategy (scanner.rs:1529-1577); similarity <= 15 is what the
-// reference's MIH serves (hamminghash.rs:5), the exact search accepts up to 63.
+// The same search over u64 hashes (impl HammingHash for u64, hamminghash.rs:23-41).  NO reference caller groups
+// u64 hashes (phash.rs is reached only from the phash_test demo); similarity <= 15 is what the
+// reference's MIH could serve for them (hamminghash.rs:5), the exact search accepts up to 63.
 inline GroupResult group_files_generic_u64(const Context &c, const std::vector<uint64_t> &hashes, uint32_t similarity,
                                            const std::vector<uint8_t> &has_hash = {},
                                            const std::vector<std::array<uint64_t, 8>> &variants = {}) {

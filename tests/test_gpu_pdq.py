@@ -151,6 +151,28 @@ def test_too_small_is_none(ctx):
 @pytest.mark.parametrize("shape", [(854, 1280, 3), (720, 1080, 3), (768, 780, 3), (1280, 854, 3), (513, 513),
                                    (1200, 900, 3), (2000, 1500), (700, 525, 4),
                                    (600, 2000, 4), (1537, 640, 3), (5, 4000, 3)])
+def test_general_box_predownsample_against_the_numpy_twin(ctx, orc):
+    """H5 again, with the comparison target the device shares no code with: the numpy twin's dense-matrix Box
+    resize (oracle/np_twin.py resize_box_u8) and its vectorised Jarosz / DCT -- hash, quality and coefficient
+    bits of the device path equal the twin's (the C oracle's tap loops resemble the device's host code)."""
+    import ctypes
+    from oracle import np_twin
+    from rupphash_b200 import pdqhash
+    libm = ctypes.CDLL("libm.so.6")
+    libm.cosf.argtypes = [ctypes.c_float]
+    libm.cosf.restype = ctypes.c_float
+    d = np_twin.dct_matrix(lambda a: np.float32(libm.cosf(float(a))))
+    for h, w, ch in ((854, 1280, 3), (1200, 900, 3), (700, 525, 4), (513, 513, 1), (600, 2000, 3)):
+        imgs = synth_images(2, h, w, seed=h + 3 * w, channels=ch)
+        arr = imgs[..., 0] if ch == 1 else imgs
+        got = pdqhash.hash_batch(np.ascontiguousarray(arr), want_coeffs=True, ctx=ctx)
+        for k in range(len(arr)):
+            c, q, _ = np_twin.pdq_features(arr[k], d)
+            assert np.array_equal(got["coeffs"][k].view(np.uint32), c.reshape(256).view(np.uint32)), (h, w, ch)
+            assert got["quality"][k] == np.float32(q)
+            assert np.array_equal(got["hash"][k], np_twin.to_hash(c))
+
+
 def test_general_box_predownsample(ctx, orc, shape):
     """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
     convolution, restated by the oracle): fixed-point horizontal + vertical passes on the device."""

@@ -234,3 +234,16 @@ def test_batch_mt_matches_single(orc):
         assert np.array_equal(out["hash"][i], orc.to_hash(c))
         assert np.array_equal(out["dihedral"][i], orc.dihedral(c))
         assert out["valid"][i] == 1
+
+
+@pytest.mark.parametrize("shape,target", [((854, 1280), (512, 341)), ((720, 1080), (512, 341)), ((1280, 854), (341, 512)),
+                                          ((513, 513), (512, 512)), ((600, 2000), (512, 153)), ((4000, 5), (1, 512)),
+                                          ((1000, 700), (358, 512)), ((768, 1024), (512, 384)), ((97, 53), (31, 57))])
+def test_box_resize_two_independent_restatements_agree(orc, shape, target):
+    """H5 (fast_image_resize Box convolution): the C oracle's sparse tap loops and the numpy twin's dense weight
+    matrix are written independently (the device's coefficient code mirrors the C oracle's, so the
+    comparison target has to be a second statement).  Neither is pinned against the real crate."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    src = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    dw, dh = target
+    assert np.array_equal(orc.resize_box_u8(src, dw, dh), np_twin.resize_box_u8(src, dw, dh))
