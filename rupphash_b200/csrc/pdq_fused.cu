@@ -153,7 +153,10 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
                 const int end = ((Lr0 + f1) * SPP) * (int)ROWB;
                 if (beg < end) l2_prefetch_row(src + beg, (uint32_t)min((int)PIECE, end - beg), pol);
             }
-            if (s + 4 * q < s_hi) *reinterpret_cast<uint2 *>(d + 4 * q * FLP) = luma8<LAYOUT, DOWN2, NW>(w0[q], w1[q]);
+            if (s + 4 * q < s_hi) {
+                RH_CHECK_IDX(s + 4 * q, FMAXL);
+                *reinterpret_cast<uint2 *>(d + 4 * q * FLP) = luma8<LAYOUT, DOWN2, NW>(w0[q], w1[q]);
+            }
         }
         s += 4 * SETS;
         p += SETS * rstep;
@@ -384,6 +387,8 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
     const int lo = max(0, r - HT), hi = min(H - 1, r + HB);
     const float cnt = (float)max(1, hi - lo + 1);   // rows in the clipped column window
     const Recip y8 = recip2(8.0f * cnt), y4 = recip2(4.0f * cnt);
+    RH_CHECK_IDX(min(ro, nL - 1), FMAXL);
+    if (store) RH_CHECK_IDX(r, P3_PITCH);
     const uint8_t *rowp = sL + (size_t)min(ro, nL - 1) * FLP;
     const float *pe = sE + min(ro, rows_out - 1);   // window sums of the six edge columns for this lane's row (edge_walk)
     float *p3col = p3t + r;

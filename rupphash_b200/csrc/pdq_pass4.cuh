@@ -5,6 +5,7 @@
 #pragma once
 #include "pdq_luma.cuh"
 #include "pdq_tail.cuh"
+#include "tma.cuh"
 
 namespace rh {
 
@@ -148,6 +149,7 @@ __device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg) {
 #pragma unroll 1
     for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
         const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
+        RH_CHECK_IDX(col * P4_PITCH + 4 * q + 3, 2 * 64 * P4_PITCH);
         cp_async16(stg + col * P4_PITCH + 4 * q, p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4));
     }
     cp_async_commit();
