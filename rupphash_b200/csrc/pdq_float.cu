@@ -19,9 +19,10 @@
 //        pass 2 is the column chain: running sum in a register for the whole image, the values that
 //        leave the window come from a ring of the last 8 pass-1 rows in shared memory; the quotient
 //        goes to a 32-row f32 band
-//   P3   one warp, lane = row of that band: the row chain across the columns (the band's pitch is odd:
-//        conflict-free), only the 64 decimated columns are divided and kept (pdqhash.rs:439) -> the
-//        per-CTA slab in L2
+//   P3   one warp, lane = row of that band, while the other seven warps convert the next band: the row chain
+//        across the columns (eight per step from two conflict-free LDS.128, leaving values in registers),
+//        the running sums of the 64 decimated columns (pdqhash.rs:439) go to the per-CTA slab in L2 and are
+//        divided by their window sizes by the whole CTA before pass 4
 //   then pass 4 over the slab and the 64x64 -> hash tail, both shared with pdq_fused.cu.
 #include "common.cuh"
 #include "pdq_pass4.cuh"
@@ -47,8 +48,12 @@ struct FloatArgs {
     unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA ("pdq.phase_clocks")
 };
 
+// pitch of the pass-2 band in floats: rows 16-byte aligned and 4 mod 32 apart, so that the row chains
+// (lane = row) read four columns with one conflict-free LDS.128
+__host__ __device__ inline int p2_pitch(int W) { return ((W + 31) & ~31) + 4; }
+
 __host__ __device__ inline size_t float_smem_bytes(int W) {
-    size_t body = (size_t)GBR * GLP + (size_t)8 * W * 4 + (size_t)GP2_ROWS * (W + 1) * 4;
+    size_t body = (size_t)GBR * GLP + (size_t)8 * W * 4 + (size_t)GP2_ROWS * p2_pitch(W) * 4;
     body = (body + 15) & ~size_t(15);
     if (body < P4_SMEM_BYTES) body = P4_SMEM_BYTES;   // the tail and pass-4 staging alias the band buffers
     return body + 16 * DCT_PITCH * 4;
@@ -151,79 +156,85 @@ __device__ __forceinline__ float2 pass1_pair(const uint8_t *row, const ColumnSet
     return make_float2(__fmaf_rn(f0, cs.y0h, __fmul_rn(f0, cs.y0l)), __fmaf_rn(f1, cs.y1h, __fmul_rn(f1, cs.y1l)));
 }
 
-// A decimated sample of the row chain: divide by the clipped window size and store.  Out of line on purpose:
-// inlined, the compiler evaluates the (IEEE) division speculatively for EVERY column of the chain.
-__device__ __noinline__ void emit_sample(float sum, int o, int W, int ht, int hb, float *dst, uint64_t pol_slab) {
-    st_slab(dst, div_count(sum, window_count(o, W, ht, hb)), pol_slab);
+// Phase P3 for one row of the pass-2 band (one lane): the row pass of box_one_d_float (pdqhash.rs:341-396) over W
+// samples with window WR.  A single warp runs this while the other seven convert the next band, so it is written
+// for one warp's latency: eight columns per step from two LDS.128, the values that leave the window come from
+// registers (WR is a compile-time constant), a window that is still filling subtracts exact zeros (no prologue),
+// and the running sums simply replace the samples they were computed from (two STS.128: no per-column test).
+// On return q[i] is the window sum after column i entered (= the sum of output column i - HB) and q[W + k] the
+// k-th shrink-phase sum; row_samples picks the 64 decimated columns out of that.
+template <int WR>
+__device__ __noinline__ void row_chain(float *q, int W) {
+    constexpr int HALF = (WR + 2) / 2, HB = HALF - 1;
+    float p[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) p[k] = 0.0f;
+    float sum = 0.0f;
+    for (int i = 0; i < W; i += 8) {
+        const float4 a = *reinterpret_cast<const float4 *>(q + i), b = *reinterpret_cast<const float4 *>(q + i + 4);
+        const float n[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float s[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {   // pdqhash.rs:380-387: add the entering sample, then subtract the leaving one
+            sum = __fsub_rn(__fadd_rn(sum, n[k]), k >= WR ? n[k - WR] : p[8 + k - WR]);
+            s[k] = sum;
+        }
+        *reinterpret_cast<float4 *>(q + i) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4 *>(q + i + 4) = make_float4(s[4], s[5], s[6], s[7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) p[k] = n[k];
+    }
+#pragma unroll
+    for (int k = 0; k < HB; k++) {      // shrink phase (pdqhash.rs:389-395): outputs W-HB .. W-1 (the band's pitch
+        sum = __fsub_rn(sum, p[8 - WR + k]);   // leaves >= 4 floats behind column W-1)
+        q[W + k] = sum;
+    }
 }
 
-// Phase P3 for one row of the pass-2 band (one lane): the row pass of box_one_d_float (pdqhash.rs:341-396)
-// over W samples with window wr, keeping the 64 decimated columns floor((2 j + 1) W / 128) (pdqhash.rs:439).
-__device__ __noinline__ void row_chain(const float *q, int W, int wr, float *slab_row, uint64_t pol_slab) {
-    // (out of line: the chain gets its own register allocation instead of competing with the whole kernel)
+// the RAW running sums of the 64 decimated columns floor((2 j + 1) W / 128) (pdqhash.rs:439) of one row -> slab;
+// they are divided by their window sizes afterwards by the whole CTA (normalize_slab)
+__device__ __forceinline__ void row_samples(const float *q, int W, int hb, float *slab_row, uint64_t pol_slab) {
+#pragma unroll 8
+    for (int j = 0; j < 64; j++) {
+        const int o = ((2 * j + 1) * W) >> 7;
+        st_slab(slab_row + (size_t)j * P3_PITCH, q[o + hb], pol_slab);   // o + hb >= W: a shrink-phase sum
+    }
+}
+
+__device__ __forceinline__ void row_chain_any(int wr, float *q, int W, float *slab_row, uint64_t pol_slab) {
+    switch (wr) {
+        case 2: row_chain<2>(q, W); break;
+        case 3: row_chain<3>(q, W); break;
+        case 4: row_chain<4>(q, W); break;
+        case 5: row_chain<5>(q, W); break;
+        case 6: row_chain<6>(q, W); break;
+        case 7: row_chain<7>(q, W); break;
+        default: row_chain<8>(q, W); break;
+    }
+    row_samples(q, W, (wr + 2) / 2 - 1, slab_row, pol_slab);
+}
+
+// The decimated pass-3 sums of the whole image -> quotients (pdqhash.rs:375, :383, :392), in place in the slab:
+// every thread of the CTA takes part, the divisor depends on the column only.
+__device__ __forceinline__ void normalize_slab(float *p3t, int W, int H, int wr) {
     const int half = (wr + 2) / 2, ht = wr - half, hb = half - 1;
-    float sum = 0.0f;
-    int j = 0, target = W >> 7;   // next decimated column
-    int i = 0;
-    for (; i < wr; i++) {            // the window fills (pdqhash.rs:366-378)
-        sum = __fadd_rn(sum, q[i]);
-        if (i - hb == target) {
-            emit_sample(sum, i - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
-            j++;
-            target = ((2 * j + 1) * W) >> 7;
-        }
-    }
-    // steady state (pdqhash.rs:380-387), four columns per step with the operands fetched ahead;
-    // `t` counts down to the next decimated column so that the test is one compare per column
-    const float *pe = q + i, *pl = q + i - wr;   // entering / leaving samples
-    float x0 = pe[0], x1 = pe[1], x2 = pe[2], x3 = pe[3];
-    float o0 = pl[0], o1 = pl[1], o2 = pl[2], o3 = pl[3];
-    int t = target - (i - hb);      // columns until the next sample (0 = this one)
-    for (; i + 3 < W; i += 4, pe += 4, pl += 4) {
-        // (reads up to 7 floats past the row: inside the band buffer)
-        const float n0 = pe[4], n1 = pe[5], n2 = pe[6], n3 = pe[7];
-        const float m0 = pl[4], m1 = pl[5], m2 = pl[6], m3 = pl[7];
-        const float s0 = __fsub_rn(__fadd_rn(sum, x0), o0);
-        const float s1 = __fsub_rn(__fadd_rn(s0, x1), o1);
-        const float s2 = __fsub_rn(__fadd_rn(s1, x2), o2);
-        const float s3 = __fsub_rn(__fadd_rn(s2, x3), o3);
-        sum = s3;
-        if (t < 4) {                 // a decimated column among these four (they are >= 1.1 columns apart: at most 4)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // one warp per decimated column (its divisor is a constant), lanes along the rows: coalesced, eight
+    // elements per lane and step with all loads issued before the first store
+    for (int j = warp; j < 64; j += FTHREADS / 32) {
+        const int cnt = window_count(((2 * j + 1) * W) >> 7, W, ht, hb);
+        const bool pow2 = (cnt & (cnt - 1)) == 0;
+        const float fc = (float)cnt, inv = 1.0f / fc;
+        float *col = p3t + (size_t)j * P3_PITCH;
+        for (int r0 = 0; r0 < H; r0 += 256) {
+            float v[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (t == k) {
-                    const float sk = k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3));
-                    emit_sample(sk, i + k - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
-                    j++;
-                    target = ((2 * j + 1) * W) >> 7;
-                    t = target - (i - hb);
-                }
-            }
-        }
-        t -= 4;
-        x0 = n0; x1 = n1; x2 = n2; x3 = n3;
-        o0 = m0; o1 = m1; o2 = m2; o3 = m3;
-    }
-    {
-        const float xs[3] = {x0, x1, x2}, os[3] = {o0, o1, o2};
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(r0 + 32 * u + lane, H - 1));
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            if (i + k < W) {
-                sum = __fsub_rn(__fadd_rn(sum, xs[k]), os[k]);
-                if (i + k - hb == target) {
-                    emit_sample(sum, i + k - hb, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
-                    j++;
-                    target = ((2 * j + 1) * W) >> 7;
-                }
+            for (int u = 0; u < 8; u++) {
+                const int r = r0 + 32 * u + lane;
+                if (r < H) __stcg(col + r, pow2 ? __fmul_rn(v[u], inv) : __fdiv_rn(v[u], fc));
             }
-        }
-    }
-    for (int oo = W - hb; oo < W; oo++) {   // shrink phase (pdqhash.rs:389-395)
-        sum = __fsub_rn(sum, q[oo - ht - 1]);
-        if (oo == target) {
-            emit_sample(sum, oo, W, ht, hb, slab_row + (size_t)j * P3_PITCH, pol_slab);
-            j++;
-            target = ((2 * j + 1) * W) >> 7;
         }
     }
 }
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
     constexpr int HALF = (WC + 2) / 2, HT = WC - HALF, HB = HALF - 1;
     const int wr = (W + 63) >> 6;                                         // pdqhash.rs:246
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int W8 = W >> 3, P2P = W + 1;
+    const int W8 = W >> 3, P2P = p2_pitch(W);
     float *p3t = a.p3t + (size_t)blockIdx.x * 64 * P3_PITCH;
     for (int idx = threadIdx.x; idx < 1024; idx += FTHREADS) sD[(idx >> 6) * DCT_PITCH + (idx & 63)] = a.dct[idx];
     PhaseClock clk;
@@ -293,30 +304,37 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
             const int r0 = max(0, i0 - HB);                       // first pass-2 row this band produces
             const int nb = (last ? H : i1 - HB) - r0;             // and how many
             if (active) {
-                for (int i = i0; i < i1; i++) {                   // luma row i enters the column windows
+                int i = i0;
+                // the first WC rows of the image: the window is still filling (pdqhash.rs:366-378)
+                for (; i < min(WC, i1); i++) {
                     const float2 x = pass1_pair(sL + (size_t)(i - i0) * GLP, cs);
-                    float2 *ring = reinterpret_cast<float2 *>(sP1 + (size_t)(i & 7) * W + c0);
                     sum0 = __fadd_rn(sum0, x.x);
                     sum1 = __fadd_rn(sum1, x.y);
-                    if (i >= WC) {                                // pdqhash.rs:380-387: add, then subtract
-                        const float2 old = *reinterpret_cast<const float2 *>(sP1 + (size_t)((i - WC) & 7) * W + c0);
-                        sum0 = __fsub_rn(sum0, old.x);
-                        sum1 = __fsub_rn(sum1, old.y);
-                    }
-                    *ring = x;
+                    *reinterpret_cast<float2 *>(sP1 + (size_t)(i & 7) * W + c0) = x;
                     if (i >= HB) {
-                        const int o = i - HB;
+                        const int o = i - HB, cnt = window_count(o, H, HT, HB);
                         float *dst = sP2 + (size_t)(o - r0) * P2P + c0;
                         RH_CHECK_IDX(o - r0, GP2_ROWS);
-                        if (i >= WC - 1) {                        // the full window (every row but the first few)
-                            dst[0] = WC_POW2 ? __fmul_rn(sum0, 1.0f / WC) : __fdiv_rn(sum0, (float)WC);
-                            dst[1] = WC_POW2 ? __fmul_rn(sum1, 1.0f / WC) : __fdiv_rn(sum1, (float)WC);
-                        } else {
-                            const int cnt = window_count(o, H, HT, HB);
-                            dst[0] = div_count(sum0, cnt);
-                            dst[1] = div_count(sum1, cnt);
-                        }
+                        dst[0] = div_count(sum0, cnt);
+                        dst[1] = div_count(sum1, cnt);
                     }
+                }
+                // steady state (pdqhash.rs:380-387): row i enters, row i - WC leaves, the full window of WC rows is
+                // divided.  No branches: the pass-1 work of consecutive rows overlaps, only the add / subtract pairs
+                // are sequential.
+                const uint8_t *lrow = sL + (size_t)(i - i0) * GLP;
+                float *dst = sP2 + (size_t)(i - HB - r0) * P2P + c0;
+#pragma unroll 4
+                for (; i < i1; i++, lrow += GLP, dst += P2P) {
+                    const float2 x = pass1_pair(lrow, cs);
+                    const float2 old = *reinterpret_cast<const float2 *>(sP1 + (size_t)((i - WC) & 7) * W + c0);
+                    sum0 = __fsub_rn(__fadd_rn(sum0, x.x), old.x);   // add, then subtract
+                    sum1 = __fsub_rn(__fadd_rn(sum1, x.y), old.y);
+                    *reinterpret_cast<float2 *>(sP1 + (size_t)(i & 7) * W + c0) = x;
+                    RH_CHECK_IDX(i - HB - r0, GP2_ROWS);
+                    *reinterpret_cast<float2 *>(dst) =
+                        make_float2(WC_POW2 ? __fmul_rn(sum0, 1.0f / WC) : __fdiv_rn(sum0, (float)WC),
+                                    WC_POW2 ? __fmul_rn(sum1, 1.0f / WC) : __fdiv_rn(sum1, (float)WC));
                 }
                 if (last) {
                     for (int o = H - HB; o < H; o++) {            // shrink phase (pdqhash.rs:389-395)
@@ -337,16 +355,23 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
             if (warp == 0) {
                 for (int base = 0; base < nb; base += 32) {
                     const int lr = base + lane;
-                    if (lr < nb) row_chain(sP2 + (size_t)lr * P2P, W, wr, p3t + r0 + lr, pol_slab);
+                    if (lr < nb) row_chain_any(wr, sP2 + (size_t)lr * P2P, W, p3t + r0 + lr, pol_slab);
                 }
+                clk.lap(PH_CHAIN);   // warp 0's own time in the row chains
             } else if (!last) {
+                long long t0 = 0;
+                if (a.phase_clk != nullptr && threadIdx.x == 32) t0 = clock64();
                 front_rows<LAYOUT, DOWN2>(src, a.row_pitch, W8, i1, min(i1 + GBR, H), sL, pol_px, (int)threadIdx.x - 32,
                                           FTHREADS - 32);
+                if (a.phase_clk != nullptr && threadIdx.x == 32)
+                    atomicAdd(a.phase_clk + PH_P4_CHAIN, (unsigned long long)(clock64() - t0));   // warp 1's time in the next band's front end
             }
             __syncthreads();
-            clk.lap(PH_CHAIN);   // ("p3 + next front")
+            clk.lap(PH_P4_STAGE);   // warp 0 waiting for the front end (or vice versa)
         }
-        // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
+        // the pass-3 sums -> quotients, then pass 4 + decimation into the tail's 64 x 64 buffer, quality / DCT / hash
+        normalize_slab(p3t, W, H, wr);
+        __syncthreads();
         pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
         __syncthreads();
         {
@@ -439,7 +464,7 @@ int pdq_float_run(rh_ctx *ctx, const uint8_t *d_px, int layout, bool down2, int6
         unsigned long long h[NPHASE];
         RH_CUDA(ctx, cudaMemcpyAsync(h, a.phase_clk, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        static const char *names[NPHASE] = {"front", "p12", "p3", "p4_stage", "p4_chain", "tail"};
+        static const char *names[NPHASE] = {"front0", "p12", "p3(warp0)", "wait+pass4", "front(warp1)", "tail"};
         unsigned long long tot = 0;
         for (int i = 0; i < NPHASE; i++) tot += h[i];
         fprintf(stderr, "[pdq_float phases] n=%lld %dx%d", (long long)n, W, H);

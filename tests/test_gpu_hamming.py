@@ -282,3 +282,76 @@ def test_group_max_dist_matches_reference_rule(ctx, orc):
         want_plain = max(orc.hamming256(hashes[pivots[g]], hashes[i]) for i in members if has_hash[i])
         assert got_plain[g] == want_plain
     assert len(scanner.group_max_dist([], hashes, [], ctx=ctx)) == 0
+
+
+def test_group_500k_similarity_40_vs_mih_oracle(ctx, orc):
+    """configs[2] size at the reference's DEFAULT similarity (40: MIH radius 2, the PF = 4 kernel)."""
+    import os
+    from rupphash_b200 import scanner
+    n = 500_000
+    hashes, low_conf = planted_hashes(n, seed=0xB200, n_clusters=5000, identical_block=1000, threshold=40)
+    labels, cnt = scanner.group_labels(hashes, 40, low_conf=low_conf, ctx=ctx)
+    ref_labels, ref_cnt, _ = orc.group_generic(hashes, 40, low_conf=low_conf, threads=os.cpu_count() or 4)
+    assert cnt == ref_cnt
+    assert np.array_equal(labels, ref_labels)
+
+
+def test_group_150k_similarity_63_vs_bruteforce(ctx, orc):
+    """The largest allowed similarity (63, the full-distance kernel) against the oracle's brute-force statement of
+    the edge rule (the MIH probe count at radius 3 makes the CPU search slower than brute force at this size)."""
+    import os
+    from rupphash_b200 import scanner
+    n = 150_000
+    hashes, low_conf = planted_hashes(n, seed=63, threshold=63)
+    labels, cnt = scanner.group_labels(hashes, 63, low_conf=low_conf, ctx=ctx)
+    ref_labels, ref_cnt, _ = orc.group_generic(hashes, 63, low_conf=low_conf, threads=os.cpu_count() or 4, use_mih=False)
+    assert cnt == ref_cnt
+    assert np.array_equal(labels, ref_labels)
+
+
+def test_group_500k_similarity_63_rows_and_closure(ctx, orc):
+    """Full size at similarity 63 through size-independent properties: (1) for 1500 sampled files the device's edge
+    list holds exactly the pairs (i, j > i) a CPU scan of that file's row of the pair matrix finds; (2) the labels
+    are the connected components of the device's own edge list; (3) comparison_count = number of edges."""
+    from rupphash_b200 import scanner
+    n = 500_000
+    hashes, low_conf = planted_hashes(n, seed=0x63, n_clusters=5000, identical_block=1000, threshold=63)
+    labels, cnt = scanner.group_labels(hashes, 63, low_conf=low_conf, ctx=ctx)
+    edges, cnt2 = scanner.edges(hashes, 63, low_conf=low_conf, cap=4_000_000, ctx=ctx)
+    assert cnt == cnt2 == len(edges)
+    assert (edges[:, 0] < edges[:, 1]).all()
+    # (1) sampled rows: files inside planted structure and random ones
+    rng = np.random.default_rng(5)
+    sample = np.unique(np.concatenate([rng.integers(0, n, 700), edges[rng.integers(0, len(edges), 800), 0]]))
+    h64 = hashes.view(np.uint64).reshape(n, 4)
+    lc = low_conf.astype(bool)
+    from_dev = {int(i): set() for i in sample}
+    sel = np.isin(edges[:, 0], sample)
+    for i, j in edges[sel]:
+        from_dev[int(i)].add(int(j))
+    for i in sample:
+        x = h64[i + 1:] ^ h64[i]
+        d = np.zeros(len(x), np.uint32)
+        for w in range(4):
+            v = x[:, w]
+            v = v - ((v >> np.uint64(1)) & np.uint64(0x5555555555555555))
+            v = (v & np.uint64(0x3333333333333333)) + ((v >> np.uint64(2)) & np.uint64(0x3333333333333333))
+            v = (v + (v >> np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+            d += ((v * np.uint64(0x0101010101010101)) >> np.uint64(56)).astype(np.uint32)
+        limit = np.where(lc[i + 1:] | lc[i], 0, 63)          # scanner.rs:1699, :1721
+        want = set((np.flatnonzero(d <= limit) + i + 1).tolist())
+        assert from_dev[int(i)] == want, int(i)
+    # (2) labels = components of the edge list (min index of the component)
+    parent = np.arange(n)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    for i, j in edges:
+        ri, rj = find(int(i)), find(int(j))
+        if ri != rj:
+            parent[max(ri, rj)] = min(ri, rj)
+    comp = np.array([find(i) for i in range(n)], np.uint32)
+    assert np.array_equal(np.asarray(labels), comp)

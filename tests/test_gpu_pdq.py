@@ -151,6 +151,22 @@ def test_too_small_is_none(ctx):
 @pytest.mark.parametrize("shape", [(854, 1280, 3), (720, 1080, 3), (768, 780, 3), (1280, 854, 3), (513, 513),
                                    (1200, 900, 3), (2000, 1500), (700, 525, 4),
                                    (600, 2000, 4), (1537, 640, 3), (5, 4000, 3)])
+def test_general_box_predownsample(ctx, orc, shape):
+    """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
+    convolution, restated by the oracle): fixed-point horizontal + vertical passes on the device."""
+    from rupphash_b200 import pdqhash
+    h, w = shape[:2]
+    ch = shape[2] if len(shape) == 3 else 1
+    imgs = synth_images(3, h, w, seed=3 * h + w, channels=ch)
+    if ch == 1:
+        imgs = imgs[..., 0]
+    layout = {3: 0, 4: 1, 1: 2}[ch]
+    want = orc.pdq_batch(imgs if ch > 1 else imgs[..., None], layout=layout, threads=4, want_coeffs=True,
+                         want_dihedral=True)
+    got = pdqhash.hash_batch(imgs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    check_exact(got, want)
+
+
 def test_general_box_predownsample_against_the_numpy_twin(ctx, orc):
     """H5 again, with the comparison target the device shares no code with: the numpy twin's dense-matrix Box
     resize (oracle/np_twin.py resize_box_u8) and its vectorised Jarosz / DCT -- hash, quality and coefficient
@@ -171,22 +187,6 @@ def test_general_box_predownsample_against_the_numpy_twin(ctx, orc):
             assert np.array_equal(got["coeffs"][k].view(np.uint32), c.reshape(256).view(np.uint32)), (h, w, ch)
             assert got["quality"][k] == np.float32(q)
             assert np.array_equal(got["hash"][k], np_twin.to_hash(c))
-
-
-def test_general_box_predownsample(ctx, orc, shape):
-    """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
-    convolution, restated by the oracle): fixed-point horizontal + vertical passes on the device."""
-    from rupphash_b200 import pdqhash
-    h, w = shape[:2]
-    ch = shape[2] if len(shape) == 3 else 1
-    imgs = synth_images(3, h, w, seed=3 * h + w, channels=ch)
-    if ch == 1:
-        imgs = imgs[..., 0]
-    layout = {3: 0, 4: 1, 1: 2}[ch]
-    want = orc.pdq_batch(imgs if ch > 1 else imgs[..., None], layout=layout, threads=4, want_coeffs=True,
-                         want_dihedral=True)
-    got = pdqhash.hash_batch(imgs, want_coeffs=True, want_dihedral=True, ctx=ctx)
-    check_exact(got, want)
 
 
 def test_single_image_api(ctx, orc):
