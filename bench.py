@@ -396,6 +396,31 @@ def main():
     kernel_ms_per_step = max_over_ranks(kernel_ms / K)
     achieved_gbs = B * ALGO_BYTES_PER_IMAGE / (kernel_ms_per_step * 1e-3) / 1e9
 
+    # ------------------------------------------------------------- PDQ, other shapes -------
+    # the same device-resident bytes viewed as other image shapes (throughput only; the pixels are the pool's):
+    # portrait planes take the float-chain fused kernel, 512 x 512 has no pre-downsample (4x fewer source
+    # bytes per plane pixel: bound by the chains, not by HBM)
+    shapes = {}
+    for name, (h, w, kernel) in {"portrait_1024x768": (1024, 768, "pdq_float_kernel"),
+                                 "square_512x512": (512, 512, "pdq_fused_kernel"),
+                                 "portrait_512x384": (512, 384, "pdq_float_kernel"),
+                                 "small_256x256": (256, 256, "pdq_float_kernel")}.items():
+        m = pool.numel() // (h * w * 3)
+        view = pool.reshape(-1)[: m * h * w * 3].reshape(m, h, w, 3)
+        oh = torch.empty((m, 32), dtype=torch.uint8, device="cuda")
+        oq = torch.empty((m,), dtype=torch.float32, device="cuda")
+        times = []
+        for rep in range(4):
+            ctx.check(L.rh_pdq_hash_batch(ctx.handle, view.data_ptr(), _lib.LAYOUT_RGB8, m, w, h, 0, 0, oh.data_ptr(),
+                                          oq.data_ptr(), None, None, None))
+            if rep:
+                times.append(ctx.last_kernel_time()[0])
+        ms = max_over_ranks(float(np.median(times)))
+        rate = m / (ms * 1e-3)
+        shapes[name] = {"images_per_s_per_gpu": rate, "images": m, "kernel": kernel,
+                        "hbm_roofline_frac": rate * (3 * h * w + 36) / 1e9 / hbm_gbs}
+        del oh, oq
+
     # ------------------------------------------------------------- PDQ, end to end ---------
     Be = min(args.e2e_batch, B)
     hp = min(args.host_pool, Be)
@@ -432,6 +457,7 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "images_per_step_per_gpu": Be, "steps": e2e_steps,
                 "matches_device_resident_hashes": same},
         "gpu_launches": int(launches),
+        "pdq_shapes": shapes,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_gbs,
                      "traffic": traffic_per_image * B if traffic_per_image else None,
