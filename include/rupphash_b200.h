@@ -237,8 +237,9 @@ int rh_group_max_dist(rh_ctx *ctx, const uint8_t *pivot_variants, const uint8_t 
  * ncclCommInitAll (NCCL is loaded with dlopen here: the library has no link-time NCCL dependency).
  *   devices   CUDA device indices, or NULL for devices 0 .. n_dev-1 (n_dev <= 0 with NULL: all)
  *   flags     RH_GROUP_NO_NCCL: exchange with cudaMemcpyPeerAsync instead of NCCL collectives
- *             RH_GROUP_STATIC_TILES: tile t belongs to GPU t mod n_dev (default: the GPUs claim tiles
- *             from one counter in the first GPU's memory with NVLink atomics -- work stealing)
+ *             RH_GROUP_STEAL_TILES: the GPUs claim tiles from one counter in the first GPU's memory with
+ *             NVLink atomics (work stealing; absorbs unequal GPUs).  Default: tile t belongs to GPU
+ *             t mod n_dev, which measured 1 % faster on 8 equal B200s (RH_GROUP_STATIC_TILES = the default)
  * Errors: RH_ENCCL when NCCL cannot be loaded / initialised; rh_group_last_error for the message.
  * A group is not thread-safe (one in-flight call); rh_group_ctx gives the per-device contexts for
  * single-device calls between group calls.
@@ -246,6 +247,7 @@ int rh_group_max_dist(rh_ctx *ctx, const uint8_t *pivot_variants, const uint8_t 
 typedef struct rh_group rh_group;
 #define RH_GROUP_NO_NCCL 1u
 #define RH_GROUP_STATIC_TILES 2u
+#define RH_GROUP_STEAL_TILES 4u
 int rh_group_create(const int *devices, int n_dev, unsigned flags, rh_group **out);
 int rh_group_destroy(rh_group *g);
 int rh_group_size(const rh_group *g);
@@ -255,7 +257,9 @@ const char *rh_group_last_error(const rh_group *g);
 int rh_group_info(const rh_group *g, int *nccl_version, int *work_stealing);
 /* Times of the last group call in ms: [0] wall time of rh_hamming_group_multi, [1] / [2] tile kernel
  * on the slowest / fastest GPU (CUDA events), [3] sum of the tile-kernel times over the GPUs,
- * [4] wall time of rh_pdq_hash_batch_multi. */
+ * [4] wall time of rh_pdq_hash_batch_multi; the first GPU's timeline of the last group call (CUDA events):
+ * [5] inputs (copies + replication), [6] dense arrays, [7] exchange of forests / counts after its tile kernel,
+ * [8] merge + copy-out, [9] first to last mark. */
 int rh_group_last_times(const rh_group *g, double *out, int n_out);
 
 /*

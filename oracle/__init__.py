@@ -345,7 +345,7 @@ def group_generic(hashes, similarity, has_hash=None, variants=None, n_variants=N
 
 
 def group_generic_sampled(hashes, similarity, chunk_stride, has_hash=None, variants=None, n_variants=None,
-                          low_conf=None, threads=1):
+                          low_conf=None, threads=1, sample_files=0):
     """bench.py timing aid (inputs whose full CPU search takes minutes): index build as usual, probes only for
     every chunk_stride-th 2000-file chunk of query files -> edge count of that sample."""
     hashes = _c(hashes, np.uint8).reshape(-1, 32)
@@ -356,10 +356,10 @@ def group_generic_sampled(hashes, similarity, chunk_stride, has_hash=None, varia
     cnt = C.c_uint64()
     L = lib()
     L.orc_group_generic_sampled.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, C.c_size_t, C.c_uint32, C.c_int, C.c_size_t,
-                                            _u32p, _u64p]
+                                            C.c_size_t, _u32p, _u64p]
     rc = L.orc_group_generic_sampled(_p(hashes, _u8p), _p(has_hash, _u8p), _p(variants, _u8p), _p(n_variants, _u8p),
-                                     _p(low_conf, _u8p), n, similarity, threads, int(chunk_stride), _p(labels, _u32p),
-                                     C.byref(cnt))
+                                     _p(low_conf, _u8p), n, similarity, threads, int(chunk_stride), int(sample_files),
+                                     _p(labels, _u32p), C.byref(cnt))
     if rc:
         raise ValueError("similarity above 63 is not supported (scanner.rs:1650-1655)")
     return int(cnt.value)

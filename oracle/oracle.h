@@ -133,11 +133,11 @@ int orc_group_generic(const uint8_t *hashes, const uint8_t *has_hash, const uint
                       uint32_t similarity, int threads, int use_mih, uint32_t *out_label,
                       uint64_t *out_edge_count, uint32_t *edges_out, size_t edges_cap);
 
-/* bench.py timing aid: only every chunk_stride-th 2000-file chunk of query files is searched */
+/* bench.py timing aid: every chunk_stride-th 2000-file chunk of query files, its first sample_files files (0 = all) */
 int orc_group_generic_sampled(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                               const uint8_t *n_variants, const uint8_t *low_conf, size_t n,
-                              uint32_t similarity, int threads, size_t chunk_stride, uint32_t *out_label,
-                              uint64_t *out_edge_count);
+                              uint32_t similarity, int threads, size_t chunk_stride, size_t sample_files,
+                              uint32_t *out_label, uint64_t *out_edge_count);
 
 /* Same edge semantics restricted to the (row-block, col-block) tiles a rank owns;
  * used by the world_size-2 gloo tests to stand in for one GPU's tile kernel.

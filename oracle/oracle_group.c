@@ -287,6 +287,7 @@ typedef struct {
     size_t n_chunks;
     size_t next;
     size_t chunk_stride; /* 1 = every 2000-file chunk (the reference); k > 1: a bounded sample, every k-th chunk */
+    size_t sample_files; /* 0 = whole chunks; m > 0: only the first m files of each searched chunk (timing sample) */
     pthread_mutex_t mu;
 } grp_job;
 
@@ -321,6 +322,7 @@ static void *grp_worker(void *arg) {
         if (chunk >= j->n_chunks) break;
         u32vec *edges = &j->chunk_edges[chunk];
         size_t lo = chunk * CHUNK_SIZE, hi = lo + CHUNK_SIZE < j->n ? lo + CHUNK_SIZE : j->n;
+        if (j->sample_files && lo + j->sample_files < hi) hi = lo + j->sample_files;
         for (size_t i = lo; i < hi; i++) {
             if (!file_has_hash(j, i)) continue; /* :1690 */
             int count;                          /* :1692-1693, :1615-1628 */
@@ -404,30 +406,32 @@ static void labels_from_parent(size_t *parent, size_t n, uint32_t *out_label) {
 static int group_generic_impl(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                               const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
                               int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
-                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride);
+                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride, size_t sample_files);
 
 int orc_group_generic(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                       const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
                       int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
                       uint32_t *edges_out, size_t edges_cap) {
     return group_generic_impl(hashes, has_hash, variants, n_variants, low_conf, n, similarity, threads, use_mih,
-                              out_label, out_edge_count, edges_out, edges_cap, 1);
+                              out_label, out_edge_count, edges_out, edges_cap, 1, 0);
 }
 
 /* Timing aid for bench.py's cpu_baseline on inputs whose full CPU search takes minutes: the same index
- * build and probe loop, but only every chunk_stride-th 2000-file chunk of query files is searched
- * (labels then describe that sample's edges only; the caller scales the probe time by the stride). */
+ * build and probe loop, but only every chunk_stride-th 2000-file chunk of query files is searched, and of each
+ * of those only its first sample_files files (0 = all): many small work units, so that the sample keeps every
+ * thread busy (labels then describe that sample's edges only; the caller scales the probe time). */
 int orc_group_generic_sampled(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                               const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
-                              int threads, size_t chunk_stride, uint32_t *out_label, uint64_t *out_edge_count) {
+                              int threads, size_t chunk_stride, size_t sample_files, uint32_t *out_label,
+                              uint64_t *out_edge_count) {
     return group_generic_impl(hashes, has_hash, variants, n_variants, low_conf, n, similarity, threads, 1, out_label,
-                              out_edge_count, NULL, 0, chunk_stride < 1 ? 1 : chunk_stride);
+                              out_edge_count, NULL, 0, chunk_stride < 1 ? 1 : chunk_stride, sample_files);
 }
 
 static int group_generic_impl(const uint8_t *hashes, const uint8_t *has_hash, const uint8_t *variants,
                               const uint8_t *n_variants, const uint8_t *low_conf, size_t n, uint32_t similarity,
                               int threads, int use_mih, uint32_t *out_label, uint64_t *out_edge_count,
-                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride) {
+                              uint32_t *edges_out, size_t edges_cap, size_t chunk_stride, size_t sample_files) {
     if (similarity > 63) return -1; /* assert scanner.rs:1650-1655 */
     for (size_t i = 0; i < n; i++) out_label[i] = (uint32_t)i;
     *out_edge_count = 0;
@@ -454,6 +458,7 @@ static int group_generic_impl(const uint8_t *hashes, const uint8_t *has_hash, co
     job.dense_to_sparse = dense_to_sparse;
     job.n_chunks = (n + CHUNK_SIZE - 1) / CHUNK_SIZE;
     job.chunk_stride = chunk_stride;
+    job.sample_files = sample_files;
     job.chunk_edges = (u32vec *)calloc(job.n_chunks + 1, sizeof(u32vec));
     pthread_mutex_init(&job.mu, NULL);
     if (threads < 1) threads = 1;

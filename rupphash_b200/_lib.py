@@ -204,7 +204,7 @@ class Context:
         return {"popc_per_s": out[0], "lop3_per_s": out[1], "h2d_gbs": out[2], "copy_gbs": out[3]}
 
 
-GROUP_NO_NCCL, GROUP_STATIC_TILES = 1, 2
+GROUP_NO_NCCL, GROUP_STATIC_TILES, GROUP_STEAL_TILES = 1, 2, 4
 
 
 class Group:
@@ -248,10 +248,11 @@ class Group:
         return {"nccl_version": v.value, "work_stealing": bool(ws.value), "n_gpus": self.size}
 
     def last_times(self) -> dict:
-        out = (C.c_double * 8)()
-        lib().rh_group_last_times(self._h, out, 8)
+        out = (C.c_double * 12)()
+        lib().rh_group_last_times(self._h, out, 12)
         return {"group_wall_ms": out[0], "tile_ms_max": out[1], "tile_ms_min": out[2], "tile_ms_sum": out[3],
-                "hash_wall_ms": out[4]}
+                "hash_wall_ms": out[4], "gpu0_inputs_ms": out[5], "gpu0_dense_arrays_ms": out[6],
+                "gpu0_exchange_ms": out[7], "gpu0_merge_copyout_ms": out[8], "gpu0_timeline_ms": out[9]}
 
     def check(self, rc: int):
         if rc == RH_OK:

@@ -5,9 +5,12 @@
 //   inputs      host buffers are cut into one slice per GPU, every GPU copies its slice over its own
 //               PCIe link and an NCCL all-gather over NVLink replicates them; a buffer that already
 //               lives on one GPU of the group is broadcast from there
-//   search      every GPU runs the persistent tile kernel of hamming.cu against ONE claim counter in
-//               GPU 0's memory (NVLink atomics, peer access): the GPUs steal tiles from a common pool,
-//               so start-up skew and clock differences between GPUs do not end in a tail
+//   search      every GPU runs the persistent tile kernel of hamming.cu on the tiles t = rank (mod n_dev),
+//               claimed by its CTAs from a local counter.  RH_GROUP_STEAL_TILES: ONE claim counter in GPU 0's
+//               memory instead (system-scope atomics over NVLink, peer access): the GPUs steal tiles from a
+//               common pool, which absorbs start-up skew and clock differences between GPUs -- measured on
+//               8 equal B200s it is 1 % slower than the static split (7.99 vs 7.91 ms per GPU at 500k
+//               hashes), so it is opt-in
 //   exchange    ncclAllGather of the n x u32 forests + ncclAllReduce of the edge counts, then the merge
 //               (rh_uf_merge's kernels) on GPU 0 and the labels go to the caller
 //
@@ -118,7 +121,8 @@ struct rh_group {
     cudaEvent_t ev_reset = nullptr;
     std::vector<cudaEvent_t> ev_forest;             // forest of device i is ready (peer-copy exchange)
     std::string err;
-    double times[8] = {};
+    double times[12] = {};
+    cudaEvent_t ev_t[4] = {};                       // GPU 0 timeline marks of the last group call
     std::mutex err_m;
     void set_err(const std::string &s) {
         std::lock_guard<std::mutex> lk(err_m);
@@ -275,7 +279,7 @@ int rh_group_create(const int *devices, int n_dev, unsigned flags, rh_group **ou
             cudaGetLastError();
         }
     }
-    g->steal = peers && !(flags & RH_GROUP_STATIC_TILES);
+    g->steal = peers && (flags & RH_GROUP_STEAL_TILES) && !(flags & RH_GROUP_STATIC_TILES);
     cudaSetDevice(g->devices[0]);
     if (cudaMalloc(&g->shared_counter, 64) != cudaSuccess ||
         cudaEventCreateWithFlags(&g->ev_reset, cudaEventDisableTiming) != cudaSuccess) {
@@ -283,6 +287,13 @@ int rh_group_create(const int *devices, int n_dev, unsigned flags, rh_group **ou
         rh_group_destroy(g);
         return RH_ECUDA;
     }
+    cudaSetDevice(g->devices[0]);
+    for (int k = 0; k < 4; k++)
+        if (cudaEventCreate(&g->ev_t[k]) != cudaSuccess) {
+            cudaGetLastError();
+            rh_group_destroy(g);
+            return RH_ECUDA;
+        }
     for (int i = 0; i < n_dev; i++) {
         cudaSetDevice(g->devices[i]);
         cudaEvent_t e = nullptr;
@@ -343,6 +354,8 @@ int rh_group_destroy(rh_group *g) {
     }
     if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
     if (g->ev_reset) cudaEventDestroy(g->ev_reset);
+    for (int k = 0; k < 4; k++)
+        if (g->ev_t[k]) cudaEventDestroy(g->ev_t[k]);
     if (g->shared_counter) cudaFree(g->shared_counter);
     for (rh_ctx *c : g->ctx) rh_ctx_destroy(c);
     delete g;
@@ -364,7 +377,7 @@ int rh_group_info(const rh_group *g, int *nccl_version, int *work_stealing) {
 
 int rh_group_last_times(const rh_group *g, double *out, int n_out) {
     if (!g || !out) return RH_EINVAL;
-    for (int i = 0; i < n_out; i++) out[i] = i < 8 ? g->times[i] : 0.0;
+    for (int i = 0; i < n_out; i++) out[i] = i < 12 ? g->times[i] : 0.0;
     return RH_OK;
 }
 
@@ -402,7 +415,7 @@ int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *ha
         return RH_EINVAL;
     }
     // the claim counter is reset before any GPU can reach its tile kernel
-    if (cudaSetDevice(g->devices[0]) != cudaSuccess ||
+    if (cudaSetDevice(g->devices[0]) != cudaSuccess || cudaEventRecord(g->ev_t[0], c0->stream) != cudaSuccess ||
         cudaMemsetAsync(g->shared_counter, 0, 64, c0->stream) != cudaSuccess ||
         cudaEventRecord(g->ev_reset, c0->stream) != cudaSuccess) {
         g->set_err("rh_hamming_group_multi: resetting the claim counter failed");
@@ -431,6 +444,7 @@ int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *ha
             }
         }
         if (g->use_nccl) RH_NCCL(g, ctx, g->nccl.GroupEnd());
+        if (i == 0) RH_CUDA(ctx, cudaEventRecord(g->ev_t[1], st));
         void *p;
         RH_TRY(scratch(ctx, S_OUT0, (size_t)n * 4, &p));
         d_forest[i] = (uint32_t *)p;
@@ -459,6 +473,7 @@ int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *ha
         } else if (world > 1) {
             RH_CUDA(ctx, cudaEventRecord(g->ev_forest[i], st));
         }
+        if (i == 0) RH_CUDA(ctx, cudaEventRecord(g->ev_t[2], st));
         return RH_OK;
     });
     if (rc != RH_OK) {
@@ -504,6 +519,7 @@ int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *ha
             e = cudaMemcpyAsync(peer_counts.data(), d_sum[0] + 1, 8 * (size_t)world, cudaMemcpyDeviceToHost, st0);
         if (e != cudaSuccess) s = fail(c0, RH_ECUDA, "copy of the edge count", e);
     }
+    cudaEventRecord(g->ev_t[3], st0);
     // the single synchronisation: GPU 0 last (its stream carries the merge)
     for (int i = world - 1; i >= 0; i--) {
         cudaSetDevice(g->devices[i]);
@@ -531,6 +547,15 @@ int rh_hamming_group_multi(rh_group *g, const uint8_t *hashes, const uint8_t *ha
     g->times[1] = tmax;   // tile kernel, slowest GPU
     g->times[2] = tmin;   // tile kernel, fastest GPU
     g->times[3] = tsum;   // GPU-milliseconds spent in the tile kernels
+    // GPU 0's timeline: inputs | dense arrays | tiles | exchange | merge + copy-out
+    cudaSetDevice(g->devices[0]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g->ev_t[0], g->ev_t[1]) == cudaSuccess) g->times[5] = ms;
+    if (cudaEventElapsedTime(&ms, g->ev_t[1], c0->ev_a) == cudaSuccess) g->times[6] = ms;
+    if (cudaEventElapsedTime(&ms, c0->ev_b, g->ev_t[2]) == cudaSuccess) g->times[7] = ms;
+    if (cudaEventElapsedTime(&ms, g->ev_t[2], g->ev_t[3]) == cudaSuccess) g->times[8] = ms;
+    if (cudaEventElapsedTime(&ms, g->ev_t[0], g->ev_t[3]) == cudaSuccess) g->times[9] = ms;
+    cudaGetLastError();
     return RH_OK;
 }
 

@@ -40,7 +40,7 @@ def test_group_of_one_matches_oracle(orc):
         g.close()
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 3])   # NCCL+stealing, peer copies, static tiles, both
+@pytest.mark.parametrize("flags", [0, 1, 4, 5])   # NCCL + static tiles, peer copies, work stealing, both
 @pytest.mark.parametrize("similarity", [31, 40])
 def test_group_all_gpus_matches_oracle(orc, flags, similarity):
     from rupphash_b200 import _lib, scanner
