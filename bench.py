@@ -468,6 +468,27 @@ def main():
                      "algorithmic_bytes_per_image": ALGO_BYTES_PER_IMAGE},
     }
 
+    # ------------------------------------------------------------- PDQ through the scanner-style feeder ----
+    # the whole host side of the reference's scan loop restructured into batches (scanner.rs:1202-1521): a pool of
+    # "decode" workers -- here a memcpy out of a PAGEABLE pool, i.e. the cost of handing a decoded image over --
+    # copies into page-locked staging batches, one submitter keeps two batches in flight (rh_pdq_hash_batch_async)
+    if rank == 0:
+        n_feed = 2048
+        pageable = [np.array(host_np[k % Be]) for k in range(64)]      # 64 distinct pageable images, cycled
+        workers = max(2, min(16, (os.cpu_count() or 4) // max(1, world)))
+        scanner.hash_files_batched(range(256), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
+                                   want_coeffs=False, ctx=ctx)       # warm-up: staging buffers, pinned allocations
+        t0 = time.perf_counter()
+        fed = scanner.hash_files_batched(range(n_feed), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
+                                         want_coeffs=False, ctx=ctx)
+        dt = time.perf_counter() - t0
+        ok = all(np.array_equal(fed[k]["hash"], res["hash"][k % 64 % Be]) for k in range(0, n_feed, 97))
+        line["e2e"]["feeder"] = {"value": n_feed / dt, "unit": "images/s", "images": n_feed, "decode_workers": workers,
+                                 "what": "scanner.hash_files_batched: memcpy 'decode' from pageable memory -> pinned staging "
+                                         "-> async H2D + kernels + D2H, results per file (1 GPU, rank 0)",
+                                 "matches_hash_batch": bool(ok)}
+        del pageable, fed
+
     # ------------------------------------------------------------- integer / copy peaks -----
     # every rank measures at the same time: the pinned-H2D figure is then the CONCURRENT rate each GPU gets
     # while its neighbours copy too -- the denominator of the N-GPU e2e number (a solo figure cannot tell a
