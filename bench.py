@@ -476,12 +476,14 @@ def main():
         n_feed = 2048
         pageable = [np.array(host_np[k % Be]) for k in range(64)]      # 64 distinct pageable images, cycled
         workers = max(2, min(16, (os.cpu_count() or 4) // max(1, world)))
-        scanner.hash_files_batched(range(256), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
-                                   want_coeffs=False, ctx=ctx)       # warm-up: staging buffers, pinned allocations
+        fdr = scanner.Feeder()
+        scanner.hash_files_batched(range(n_feed), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
+                                   want_coeffs=False, ctx=ctx, feeder=fdr)   # warm-up: page-locks the staging buffers
         t0 = time.perf_counter()
         fed = scanner.hash_files_batched(range(n_feed), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
-                                         want_coeffs=False, ctx=ctx)
+                                         want_coeffs=False, ctx=ctx, feeder=fdr)
         dt = time.perf_counter() - t0
+        fdr.close()
         ok = all(np.array_equal(fed[k]["hash"], res["hash"][k % 64 % Be]) for k in range(0, n_feed, 97))
         line["e2e"]["feeder"] = {"value": n_feed / dt, "unit": "images/s", "images": n_feed, "decode_workers": workers,
                                  "what": "scanner.hash_files_batched: memcpy 'decode' from pageable memory -> pinned staging "

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
         // the pass-3 sums -> quotients, then pass 4 + decimation into the tail's 64 x 64 buffer, quality / DCT / hash
         normalize_slab(p3t, W, H, wr);
         __syncthreads();
-        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
+        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, ts.p4_bar, clk);
         __syncthreads();
         {
             const int lines = (H * 4 + 127) / 128;

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             clk.lap(PH_CHAIN);
         }
         // pass 4 + decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
-        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, clk);
+        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, ts.p4_bar, clk);
         __syncthreads();
         clk.lap(PH_P4_STAGE);   // (the last gather)
         if (!(a.variant & 4)) {

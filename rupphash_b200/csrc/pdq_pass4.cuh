@@ -145,27 +145,43 @@ __device__ __forceinline__ void p4_gather(const float *stage, const float *shr, 
 
 // plane rows [c0, c0 + P4_ROWS) of the 64 columns -> stg (rows past H are copied but never used;
 // the clamp keeps the last chunk inside its column)
-__device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg) {
-#pragma unroll 1
-    for (int idx = threadIdx.x; idx < 64 * (P4_ROWS / 4); idx += FTHREADS) {
-        const int col = idx / (P4_ROWS / 4), q = idx % (P4_ROWS / 4);
-        RH_CHECK_IDX(col * P4_PITCH + 4 * q + 3, 2 * 64 * P4_PITCH);
-        cp_async16(stg + col * P4_PITCH + 4 * q, p3t + (size_t)col * P3_PITCH + min(c0 + 4 * q, P3_PITCH - 4));
+// plane rows [c0, c0 + P4_ROWS) of the 64 slab columns -> stg, by the bulk-copy engine: one 512-byte
+// cp.async.bulk per column (threads 0..63, each arming the stage's mbarrier with its own byte count), instead of
+// 2048 16-byte cp.async requests per chunk.  c0 is a multiple of P4_ROWS and P3_PITCH = 4 P4_ROWS, so a chunk never
+// leaves its column (rows past H are copied but never used).
+static_assert(P3_PITCH % P4_ROWS == 0, "a staged chunk stays inside its slab column");
+__device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg, uint64_t *bar) {
+    if (threadIdx.x < 64) {
+        const int col = threadIdx.x;
+        RH_CHECK_IDX(c0 + P4_ROWS - 1, P3_PITCH);
+        mbar_arrive_expect_tx(bar, P4_ROWS * 4);
+        bulk_g2s(stg + col * P4_PITCH, p3t + (size_t)col * P3_PITCH + c0, P4_ROWS * 4, bar);
     }
-    cp_async_commit();
 }
 
 template <int WC>
-__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, PhaseClock &clk) {
+__device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, unsigned long long *bars,
+                                      PhaseClock &clk) {
     constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
     const int j = threadIdx.x;
     float sum = 0.0f;
     float prev[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) prev[k] = 0.0f;
-    p4_issue(p3t, 0, stage);
-    if (P4_ROWS < H) p4_issue(p3t, P4_ROWS, stage + 64 * P4_PITCH);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(bars);
+    // the slab was written with ordinary stores by this CTA: order them before the copy engine's reads, and set up
+    // the two stage barriers (64 arrivals: one per issuing thread) in memory the band buffers used until now
+    fence_proxy_async_all();
+    if (j == 0) {
+        mbar_init(&bar[0], 64);
+        mbar_init(&bar[1], 64);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    p4_issue(p3t, 0, stage, &bar[0]);
+    if (P4_ROWS < H) p4_issue(p3t, P4_ROWS, stage + 64 * P4_PITCH, &bar[1]);
     int buf = 0;
+    uint32_t parity = 0;   // bit b: phase of stage b's barrier
     for (int c0 = 0; c0 < H; c0 += P4_ROWS, buf ^= 1) {
         float *stg = stage + buf * (64 * P4_PITCH);
         const int rows = min(P4_ROWS, H - c0);
@@ -176,11 +192,8 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
 #pragma unroll
             for (int k = 0; k < HB; k++) leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
         }
-        if (last)
-            cp_async_wait<0>();
-        else
-            cp_async_wait<1>();   // everything but the chunk after this one has landed
-        __syncthreads();
+        mbar_wait(&bar[buf], (parity >> buf) & 1u);   // this chunk has landed (the next one is still in flight)
+        parity ^= 1u << buf;
         clk.lap(PH_P4_STAGE);
         if (j < 64) {
             p4_walk<WC>(stg + j * P4_PITCH, c0, rows, sum, prev);
@@ -193,14 +206,20 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
                     shr[k * 64 + j] = sum;
                 }
             }
+            fence_proxy_async();   // the in-place sums are ordered before a later bulk copy into this stage
         }
         __syncthreads();
         clk.lap(PH_P4_CHAIN);
         p4_gather<WC>(stg, shr, H, c0, rows, last, B);
         if (c0 + 2 * P4_ROWS < H) {   // this buffer takes the chunk after the next one
             __syncthreads();
-            p4_issue(p3t, c0 + 2 * P4_ROWS, stg);
+            p4_issue(p3t, c0 + 2 * P4_ROWS, stg, &bar[buf]);
         }
+    }
+    __syncthreads();
+    if (j == 0) {   // the barriers' memory goes back to the band buffers
+        mbar_inval(&bar[0]);
+        mbar_inval(&bar[1]);
     }
 }
 

@@ -33,6 +33,7 @@ struct TailSmem {
     uint8_t bits[4][256];        // one bit per coefficient and sign pattern
     int red[8];
     float median;
+    unsigned long long p4_bar[2];   // mbarriers of the pass-4 staging buffers (fused kernels only)
 };
 
 struct TailOut {

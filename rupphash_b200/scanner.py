@@ -343,8 +343,25 @@ class _DeviceHasher:
         return res
 
 
+class Feeder:
+    """Keeps the feeder's page-locked staging and result buffers between hash_files_batched calls (page-locking a
+    256 MB batch costs ~0.1 s: a scan that runs in several calls, or a benchmark's timed repeat, should not pay
+    it again).  close() releases everything."""
+
+    def __init__(self, pinned: bool = True):
+        self.pool = _PinnedPool(bool(pinned))
+        self.free_bufs = {}
+        self.device_hasher = None
+
+    def close(self):
+        self.pool.close()
+        self.free_bufs = {}
+        self.device_hasher = None
+
+
 def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progress=None, depth=2, hasher=None,
-                       pinned=None, decode=None, workers=0, batch_bytes=256 << 20, max_open_shapes=8, inflight=2):
+                       pinned=None, decode=None, workers=0, batch_bytes=256 << 20, max_open_shapes=8, inflight=2,
+                       feeder=None):
     """Scanner-style feeder (scanner.rs:1202-1521 restructured): files are decoded on the host (as in the
     reference), same-sized images are collected into batches, hashed on the device, and handed back in
     arrival order as dicts(hash, quality, quality_100, coeffs) -- or None where the reference returns None
@@ -361,19 +378,22 @@ def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progre
              rh_pdq_hash_batch_async so that the copy of batch k+1 runs under the kernels of batch k.
     progress ticks (scanner.rs:1206-1211) fire per finished batch as progress(done, seen).
     `hasher(batch_array) -> hash_batch-style dict` replaces the device (CPU tests); `pinned` defaults to True
-    with the device."""
+    with the device.  `feeder` (a Feeder) keeps the page-locked buffers for the next call."""
     import queue
     import threading
     device = hasher is None
     if device:
         ctx = ctx or default_context()
         pinned = True if pinned is None else pinned
-    pool = _PinnedPool(bool(pinned))
+    own_feeder = feeder is None
+    if feeder is None:
+        feeder = Feeder(bool(pinned))
+    pool = feeder.pool
     results, failure = {}, []
     seen = [0]
     lock = threading.Condition()
     work = queue.Queue(maxsize=max(1, depth))
-    free_bufs = {}            # (cap, shape) -> [staging arrays]
+    free_bufs = feeder.free_bufs   # (cap, shape) -> [staging arrays]
     open_slots = {}           # shape -> _Slot
     stamp = [0]
 
@@ -411,7 +431,9 @@ def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progre
                 if device:
                     if dev is None:
                         cap = max(1, min(batch_size, 1 << 16))
-                        dev = _DeviceHasher(ctx, want_coeffs, pool, cap)
+                        dev = feeder.device_hasher
+                        if dev is None or dev.max_images < cap or dev.want_coeffs != want_coeffs or dev.ctx is not ctx:
+                            dev = feeder.device_hasher = _DeviceHasher(ctx, want_coeffs, pool, cap)
                     pending.append((dev.submit(arr), slot))
                     if len(pending) >= max(1, inflight):
                         h, s = pending.pop(0)
@@ -548,7 +570,8 @@ def hash_files_batched(items, batch_size=256, want_coeffs=True, ctx=None, progre
         done_feeding[0] = True
         work.put(None)
         th.join()
-        pool.close()
+        if own_feeder:
+            feeder.close()
     if failure:
         raise failure[0]
     return [results[i] for i in range(seen[0])]
