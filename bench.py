@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--skip-hamming", action="store_true")
     ap.add_argument("--skip-worstcase", action="store_true")
     ap.add_argument("--skip-config5", action="store_true")
+    ap.add_argument("--skip-config4", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-peaks", action="store_true")
     return ap.parse_args()
@@ -421,6 +422,11 @@ def main():
                         "hbm_roofline_frac": rate * (3 * h * w + 36) / 1e9 / hbm_gbs}
         del oh, oq
 
+    # ------------------------------------------------------------- configs[3]: 512 x 512, 8 variants + pHash ----
+    config4 = None
+    if rank == 0 and not args.skip_config4:
+        config4 = bench_config4(torch, _lib, pdqhash, scanner, ctx, pool, hbm_gbs, args)
+
     # ------------------------------------------------------------- PDQ, end to end ---------
     Be = min(args.e2e_batch, B)
     hp = min(args.host_pool, Be)
@@ -458,6 +464,7 @@ def main():
                 "matches_device_resident_hashes": same},
         "gpu_launches": int(launches),
         "pdq_shapes": shapes,
+        "config4": config4,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_gbs,
                      "traffic": traffic_per_image * B if traffic_per_image else None,
@@ -638,6 +645,116 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config4(torch, _lib, pdqhash, scanner, ctx, pool, hbm_gbs, args):
+    """configs[3]: PDQ with all 8 dihedral variants (+ coefficients) and the 64-bit pHash over 512 x 512 images, then
+    grouping across the variants.  The images are the device-resident pool viewed as 512 x 512 (throughput); parity
+    samples go through the CPU oracle.  The 1M x 8 PDQ grouping itself is the `config5` section (same input shape);
+    here: u64 grouping of the pHashes with phash::generate_dihedral_hashes variants -- offered for symmetry with
+    `impl HammingHash for u64` (hamminghash.rs:23-41); NO reference caller groups u64 hashes."""
+    from rupphash_b200 import phash
+    L = _lib.lib()
+    h = w = 512
+    m = min(pool.numel() // (h * w * 3), 8192)
+    view = pool.reshape(-1)[: m * h * w * 3].reshape(m, h, w, 3)
+    oh = torch.empty((m, 32), dtype=torch.uint8, device="cuda")
+    oq = torch.empty((m,), dtype=torch.float32, device="cuda")
+    oc = torch.empty((m, 256), dtype=torch.float32, device="cuda")
+    od = torch.empty((m, 8, 32), dtype=torch.uint8, device="cuda")
+    ms = []
+    for rep in range(4):
+        ctx.check(L.rh_pdq_hash_batch(ctx.handle, view.data_ptr(), _lib.LAYOUT_RGB8, m, w, h, 0, 0, oh.data_ptr(), oq.data_ptr(),
+                                      oc.data_ptr(), od.data_ptr(), None))
+        ms.append(ctx.last_kernel_time()[0])
+    t_pdq = float(np.median(ms[1:])) * 1e-3
+    ph = torch.empty((m,), dtype=torch.int64, device="cuda")
+    pd8 = torch.empty((m, 8), dtype=torch.int64, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tp = []
+    for rep in range(4):
+        ev0.record(torch.cuda.current_stream())
+        ctx.check(L.rh_phash_batch(ctx.handle, view.data_ptr(), _lib.LAYOUT_RGB8, m, w, h, 0, 0, ph.data_ptr(), pd8.data_ptr()))
+        ev1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        tp.append(ev0.elapsed_time(ev1))
+    t_ph = float(np.median(tp[1:])) * 1e-3
+    out = {"image": [h, w, 3], "images": m,
+           "pdq_8_variants_coeffs": {"images_per_s": m / t_pdq,
+                                     "hbm_roofline_frac": (m / t_pdq) * (3 * h * w + 36 + 1024 + 224) / 1e9 / hbm_gbs,
+                                     "outputs": "hash + quality + 256 coefficients + 8 dihedral hashes per image"},
+           "phash_8_variants": {"images_per_s": m / t_ph, "hbm_roofline_frac": (m / t_ph) * (3 * h * w + 72) / 1e9 / hbm_gbs,
+                                "note": "phash.rs:48-83 on the device; parity with the `image` / `rustdct` crates unpinned"}}
+    if not args.skip_cpu:
+        import oracle
+        oracle.build()
+        k = 32
+        host = view[:k].cpu().numpy()
+        ref = oracle.pdq_batch(host, threads=min(k, os.cpu_count() or 1), want_coeffs=True, want_dihedral=True)
+        out["pdq_8_variants_coeffs"]["parity_vs_oracle"] = {
+            "images": k, "hash": bool(np.array_equal(oh[:k].cpu().numpy(), ref["hash"])),
+            "dihedral": bool(np.array_equal(od[:k].cpu().numpy(), ref["dihedral"])),
+            "coefficient_bits": bool(np.array_equal(oc[:k].cpu().numpy().view(np.uint32), ref["coeffs"].view(np.uint32)))}
+        want = np.array([oracle.phash_image(host[i])[0] for i in range(k)], np.uint64)
+        got = ph[:k].cpu().numpy().view(np.uint64)
+        out["phash_8_variants"]["parity_vs_oracle"] = {
+            "images": k, "hash": bool(np.array_equal(got, want)),
+            "dihedral": bool(all(list(pd8[i].cpu().numpy().view(np.uint64)) == oracle.phash_dihedral(int(want[i])) for i in range(k)))}
+    # u64 grouping across the 8 pHash variants: 1M synthetic 64-bit hashes with planted near-duplicates
+    n = 1_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(64)
+    base = torch.randint(-(1 << 62), 1 << 62, (n,), generator=g, device="cuda", dtype=torch.int64)
+    src = torch.randint(0, n, (n // 50,), generator=g, device="cuda")
+    dst = torch.randint(0, n, (n // 50,), generator=g, device="cuda")
+    flips = torch.randint(0, 64, (n // 50, 3), generator=g, device="cuda")
+    mask = (torch.ones_like(flips) << flips).sum(dim=1)     # up to 3 bits flipped (a repeated position counts twice: fine)
+    base[dst] = base[src] ^ mask
+    hv = base.cpu().numpy().view(np.uint64)
+    var = np.empty((n, 8), np.uint64)
+    # the 8 bit-level variants of every hash on the host (pure bit permutations, phash.rs:242-255), vectorised
+    bits = ((hv[:, None] >> np.arange(63, -1, -1, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(n, 8, 8)
+    xs, ys = np.meshgrid(np.arange(8), np.arange(8))
+
+    def pack(bm):
+        return (bm.reshape(n, 64).astype(np.uint64) << np.arange(63, -1, -1, dtype=np.uint64)[None, :]).sum(axis=1, dtype=np.uint64)
+    odd_x, odd_y, odd_xy = (xs % 2 == 1), (ys % 2 == 1), ((xs + ys) % 2 == 1)
+
+    def r90(bm):
+        return np.where(odd_x[None], 1 - bm.transpose(0, 2, 1), bm.transpose(0, 2, 1))
+
+    def r180(bm):
+        return np.where(odd_xy[None], 1 - bm, bm)
+
+    def r270(bm):
+        return np.where(odd_y[None], 1 - bm.transpose(0, 2, 1), bm.transpose(0, 2, 1))
+    fl = np.where(odd_x[None], 1 - bits, bits)
+    for kk, bm in enumerate((bits, r90(bits), r180(bits), r270(bits), fl, r90(fl), r180(fl), r270(fl))):
+        var[:, kk] = pack(bm)
+    ok_variants = all(list(var[i]) == phash.generate_dihedral_hashes(int(hv[i])) for i in range(0, n, n // 16))
+    d_h = torch.from_numpy(hv.view(np.int64)).cuda()
+    d_v = torch.from_numpy(var.view(np.int64)).cuda()
+    lab = torch.empty(n, dtype=torch.int32, device="cuda")
+    import ctypes as C
+    cnt = C.c_uint64()
+    walls = []
+    ctx.check(L.rh_hamming_group_u64(ctx.handle, d_h.data_ptr(), None, d_v.data_ptr(), None, None, 20000, 10, lab.data_ptr(),
+                                     C.byref(cnt)))    # warm-up on a prefix
+    for rep in range(1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.check(L.rh_hamming_group_u64(ctx.handle, d_h.data_ptr(), None, d_v.data_ptr(), None, None, n, 10, lab.data_ptr(),
+                                         C.byref(cnt)))
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    labn = lab.cpu().numpy()
+    out["phash_grouping_u64"] = {"n_hashes": n, "variants": 8, "similarity": 10, "pairs": 8 * n * (n - 1) // 2,
+                                 "group_wall_ms": min(walls) * 1e3, "pairs_per_s": 8 * n * (n - 1) / 2 / min(walls),
+                                 "edges": int(cnt.value), "groups": int((np.bincount(labn, minlength=n) > 1).sum()),
+                                 "variant_rule_matches_rh_phash_dihedral": bool(ok_variants),
+                                 "note": "no reference caller groups u64 hashes; parity of rh_hamming_group_u64 vs brute force "
+                                         "is tests/test_gpu_hamming.py::test_u64_group_and_find_groups_kats"}
+    return out
 
 
 def pinned(torch, arr):

@@ -520,6 +520,10 @@ int launch_fused(rh_ctx *ctx, const FusedArgs &a, int grid) {
     const bool packed = a.row_pitch == (size_t)FW * (DOWN2 ? 2 : 1) * CH;
     auto kern = packed ? pdq_fused_kernel<LAYOUT, DOWN2, WC, true> : pdq_fused_kernel<LAYOUT, DOWN2, WC, false>;
     RH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSMEM));
+    // the per-SM turn locks start free (a launch that died holding one must not block the next)
+    void *locks = nullptr;
+    RH_CUDA(ctx, cudaGetSymbolAddress(&locks, g_front_lock));
+    RH_CUDA(ctx, cudaMemsetAsync(locks, 0, sizeof(g_front_lock), ctx->stream));
     kern<<<grid, FTHREADS, FSMEM, ctx->stream>>>(a);
     RH_LAUNCHED(ctx, "pdq_fused_kernel");
     return RH_OK;
