@@ -4,10 +4,18 @@
 // std::optional<T>, panics become exceptions thrown on the HOST side of the ABI only.
 #pragma once
 #include <array>
+#include <condition_variable>
 #include <cstdint>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
+#include <tuple>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -280,6 +288,278 @@ inline std::vector<uint32_t> group_max_dist(const Context &c, const std::vector<
                               (int64_t)member_hashes.size(), (int64_t)pivot_variants.size(), out.data()));
     return out;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// The hash loop of scan_and_group (scanner.rs:1202-1521) restructured into batches, natively: the caller's
+// decode workers (the reference's rayon pool, scanner.rs:1188-1205) call push() concurrently with decoded
+// images of any size; same-sized images are copied into page-locked staging batches (capped by count and
+// by bytes, at most `max_open_shapes` partly filled batches); ONE submitter thread owns the rh_ctx and
+// keeps `inflight` batches queued with rh_pdq_hash_batch_async, handing every result to `on_result`
+// (called on the submitter thread: the DbUpdate fan-out of scanner.rs:1495-1518).  finish() flushes the
+// partial batches and joins.  Images smaller than 5 x 5 are reported with valid = false (pdqhash.rs:167-169).
+struct FileHash {
+    size_t index;       // the caller's file index
+    bool valid;         // false = the reference's None
+    pdqhash::Hash hash;
+    float quality;
+    uint16_t quality_100;
+    std::array<float, RH_PDQ_COEFFS> coefficients;   // filled when want_coeffs
+};
+
+class BatchFeeder {
+public:
+    using ResultFn = std::function<void(const FileHash &)>;
+    BatchFeeder(Context &ctx, ResultFn on_result, bool want_coeffs = true, size_t batch_images = 256,
+                size_t batch_bytes = size_t(256) << 20, size_t max_open_shapes = 8, size_t inflight = 2)
+        : ctx_(ctx), on_result_(std::move(on_result)), want_coeffs_(want_coeffs), batch_images_(batch_images),
+          batch_bytes_(batch_bytes), max_open_(max_open_shapes), inflight_(inflight ? inflight : 1) {
+        submitter_ = std::thread([this] { run(); });
+    }
+    ~BatchFeeder() {
+        try {
+            finish();
+        } catch (...) {
+        }
+        for (auto &kv : free_)
+            for (Batch *b : kv.second) release(b);
+    }
+    BatchFeeder(const BatchFeeder &) = delete;
+    BatchFeeder &operator=(const BatchFeeder &) = delete;
+
+    // thread-safe; copies the pixels (rows must be tight: width * channels bytes)
+    void push(size_t index, const ImageView &img) {
+        const int ch = img.layout == RH_LAYOUT_RGB8 ? 3 : (img.layout == RH_LAYOUT_RGBA8 ? 4 : 1);
+        if (img.width < 5 || img.height < 5) {
+            FileHash r{};
+            r.index = index;
+            std::lock_guard<std::mutex> lk(small_m_);
+            small_.push_back(r);
+            return;
+        }
+        const size_t bytes = (size_t)img.width * img.height * ch;
+        const Key key{img.width, img.height, (int)img.layout};
+        Batch *b = nullptr, *evicted = nullptr;
+        size_t slot = 0;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            if (failed_) throw std::runtime_error(error_);
+            auto it = open_.find(key);
+            if (it == open_.end()) {
+                if (open_.size() >= max_open_) {   // send the least recently used partial batch early
+                    auto lru = open_.begin();
+                    for (auto j = open_.begin(); j != open_.end(); ++j)
+                        if (j->second->stamp < lru->second->stamp) lru = j;
+                    evicted = lru->second;
+                    open_.erase(lru);
+                }
+                size_t cap = batch_bytes_ / bytes;
+                if (cap < 1) cap = 1;
+                if (cap > batch_images_) cap = batch_images_;
+                b = acquire(key, cap, bytes);
+                open_[key] = b;
+            } else
+                b = it->second;
+            slot = b->idx.size();
+            b->idx.push_back(index);
+            b->stamp = ++stamp_;
+            if (b->idx.size() >= b->cap) open_.erase(key);
+        }
+        std::memcpy(b->pixels + slot * bytes, img.pixels, bytes);   // outside the lock: the workers copy in parallel
+        bool full;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            b->filled++;
+            full = b->idx.size() >= b->cap && b->filled == b->idx.size();
+            cv_fill_.notify_all();
+        }
+        if (evicted) enqueue(evicted);
+        if (full) enqueue(b);
+    }
+
+    // flush the partial batches, wait for every result; rethrows a device error
+    void finish() {
+        if (!submitter_.joinable()) return;
+        std::vector<Batch *> rest;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (auto &kv : open_) rest.push_back(kv.second);
+            open_.clear();
+        }
+        for (Batch *b : rest) enqueue(b);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            done_ = true;
+            cv_work_.notify_all();
+        }
+        submitter_.join();
+        for (const FileHash &r : small_) on_result_(r);
+        small_.clear();
+        if (failed_) throw std::runtime_error(error_);
+    }
+
+private:
+    struct Key {
+        int w, h, layout;
+        bool operator<(const Key &o) const { return std::tie(w, h, layout) < std::tie(o.w, o.h, o.layout); }
+    };
+    struct Batch {
+        Key key;
+        size_t cap = 0, bytes = 0, filled = 0;
+        uint64_t stamp = 0, ticket = 0;
+        uint8_t *pixels = nullptr;   // page-locked: cap images
+        uint8_t *hash = nullptr, *valid = nullptr;
+        float *quality = nullptr, *coeffs = nullptr;
+        std::vector<size_t> idx;
+    };
+    Batch *acquire(const Key &key, size_t cap, size_t bytes) {   // under m_
+        auto &pool = free_[std::make_pair(key, cap)];
+        if (!pool.empty()) {
+            Batch *b = pool.back();
+            pool.pop_back();
+            b->idx.clear();
+            b->filled = 0;
+            return b;
+        }
+        Batch *b = new Batch();
+        b->key = key;
+        b->cap = cap;
+        b->bytes = bytes;
+        void *p = nullptr;
+        const size_t res = cap * (32 + 1 + 4 + (want_coeffs_ ? RH_PDQ_COEFFS * 4 : 0));
+        if (rh_alloc_pinned(cap * bytes + res + 64, &p) != RH_OK) {
+            delete b;
+            throw std::bad_alloc();
+        }
+        b->pixels = (uint8_t *)p;
+        uint8_t *q = b->pixels + ((cap * bytes + 15) & ~size_t(15));
+        b->quality = (float *)q;
+        q += cap * 4;
+        if (want_coeffs_) {
+            b->coeffs = (float *)q;
+            q += cap * RH_PDQ_COEFFS * 4;
+        }
+        b->hash = q;
+        q += cap * 32;
+        b->valid = q;
+        return b;
+    }
+    void release(Batch *b) {
+        rh_free_pinned(b->pixels);
+        delete b;
+    }
+    void enqueue(Batch *b) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_fill_.wait(lk, [&] { return b->filled == b->idx.size(); });   // copies still in progress
+        if (b->idx.empty()) {
+            free_[std::make_pair(b->key, b->cap)].push_back(b);
+            return;
+        }
+        cv_work_.wait(lk, [&] { return work_.size() < 2 * inflight_ || failed_; });   // back-pressure on the decoders
+        work_.push_back(b);
+        cv_work_.notify_all();
+    }
+    void publish(Batch *b) {
+        for (size_t k = 0; k < b->idx.size(); k++) {
+            FileHash r{};
+            r.index = b->idx[k];
+            r.valid = b->valid[k] != 0;
+            if (r.valid) {
+                std::memcpy(r.hash.data(), b->hash + 32 * k, 32);
+                r.quality = b->quality[k];
+                r.quality_100 = quality_100(r.quality);
+                if (want_coeffs_) std::memcpy(r.coefficients.data(), b->coeffs + RH_PDQ_COEFFS * k, RH_PDQ_COEFFS * 4);
+            }
+            on_result_(r);
+        }
+        std::lock_guard<std::mutex> lk(m_);
+        free_[std::make_pair(b->key, b->cap)].push_back(b);
+    }
+    void run() {
+        std::deque<Batch *> pending;
+        for (;;) {
+            Batch *b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return !work_.empty() || done_; });
+                if (work_.empty()) break;
+                b = work_.front();
+                work_.pop_front();
+                cv_work_.notify_all();
+            }
+            if (failed_) continue;
+            int rc = rh_pdq_hash_batch_async(ctx_.get(), b->pixels, b->key.layout, (int64_t)b->idx.size(), b->key.w, b->key.h, 0, 0,
+                                             b->hash, b->quality, b->coeffs, nullptr, b->valid, &b->ticket);
+            if (rc != RH_OK) {
+                fail(rh_last_error(ctx_.get()));
+                continue;
+            }
+            pending.push_back(b);
+            if (pending.size() >= inflight_) drain_one(pending);
+        }
+        while (!pending.empty() && !failed_) drain_one(pending);
+        if (failed_) rh_ctx_sync(ctx_.get());
+    }
+    void drain_one(std::deque<Batch *> &pending) {
+        Batch *b = pending.front();
+        pending.pop_front();
+        if (rh_ctx_wait(ctx_.get(), b->ticket) != RH_OK) {
+            fail(rh_last_error(ctx_.get()));
+            return;
+        }
+        publish(b);
+    }
+    void fail(const char *msg) {
+        std::lock_guard<std::mutex> lk(m_);
+        failed_ = true;
+        error_ = msg;
+        cv_work_.notify_all();
+    }
+
+    Context &ctx_;
+    ResultFn on_result_;
+    bool want_coeffs_;
+    size_t batch_images_, batch_bytes_, max_open_, inflight_;
+    std::mutex m_, small_m_;
+    std::condition_variable cv_work_, cv_fill_;
+    std::map<Key, Batch *> open_;
+    std::map<std::pair<Key, size_t>, std::vector<Batch *>> free_;
+    std::deque<Batch *> work_;
+    std::vector<FileHash> small_;
+    uint64_t stamp_ = 0;
+    bool done_ = false, failed_ = false;
+    std::string error_;
+    std::thread submitter_;
+};
+
+// Every GPU of the box from this one process (rh_group): what group_with_pdqhash (scanner.rs:1827-1832) calls.
+class Group {
+public:
+    explicit Group(int n_dev = 0, unsigned flags = 0) {
+        if (rh_group_create(nullptr, n_dev, flags, &g_) != RH_OK)
+            throw std::runtime_error("rh_group_create failed (no CUDA devices, no peer access, or NCCL unavailable)");
+    }
+    ~Group() { rh_group_destroy(g_); }
+    Group(const Group &) = delete;
+    Group &operator=(const Group &) = delete;
+    int size() const { return rh_group_size(g_); }
+    GroupResult group_files_generic(const std::vector<pdqhash::Hash> &hashes, uint32_t similarity,
+                                    const std::vector<uint8_t> &has_hash = {},
+                                    const std::vector<std::array<pdqhash::Hash, 8>> &variants = {},
+                                    const std::vector<uint8_t> &low_conf = {}) const {
+        const size_t n = hashes.size();
+        std::vector<uint32_t> label(n ? n : 1);
+        uint64_t count = 0;
+        int rc = rh_hamming_group_multi(g_, n ? hashes[0].data() : nullptr, has_hash.empty() ? nullptr : has_hash.data(),
+                                        variants.empty() ? nullptr : variants[0][0].data(), nullptr,
+                                        low_conf.empty() ? nullptr : low_conf.data(), (int64_t)n, similarity, label.data(), &count);
+        if (rc == RH_EINVAL) throw std::invalid_argument(rh_group_last_error(g_));
+        if (rc != RH_OK) throw std::runtime_error(rh_group_last_error(g_));
+        return detail::groups_from_labels(label, n, count);
+    }
+
+private:
+    rh_group *g_ = nullptr;
+};
 
 }  // namespace scanner
 }  // namespace rupphash

@@ -18,7 +18,7 @@ def _build():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     so_dir = os.path.join(ROOT, "rupphash_b200")
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", os.path.join(HOST, "harness.cpp"), "-o", EXE,
-                    "-L" + so_dir, "-lrupphash_b200", "-Wl,-rpath," + so_dir], check=True, capture_output=True)
+                    "-L" + so_dir, "-lrupphash_b200", "-Wl,-rpath," + so_dir, "-pthread"], check=True, capture_output=True)
 
 
 def test_host_mirror_compiles_and_links():
