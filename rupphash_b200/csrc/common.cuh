@@ -38,7 +38,7 @@ struct rh_ctx {
     int force_prefilter = -1;      // "hamming.prefilter": -1 = by threshold, 0 / 3 / 4 = pin the variant
     int pdq_force_generic = 0;     // "pdq.force_generic"
     int pdq_prefetch = 2;          // "pdq.prefetch": L2 prefetch mode of the fused kernel's front end
-    int pdq_prefetch_rows = 16;    // "pdq.prefetch_rows"
+    int pdq_prefetch_rows = 32;    // "pdq.prefetch_rows"
     int pdq_phase_clocks = 0;      // "pdq.phase_clocks": print per-phase cycle shares after each fused launch
     int pdq_variant = 0;           // "pdq.variant": 0 = default front end, other values = experiments
     static constexpr int kTickets = 8;   // completion events of the asynchronous calls (rh_ctx_wait)

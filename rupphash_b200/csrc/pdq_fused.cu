@@ -77,7 +77,7 @@ __device__ __forceinline__ void l2_prefetch_row(const uint8_t *p, uint32_t bytes
     asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
 
-constexpr int PF_ROWS = 16;   // plane rows between the L2 prefetch front and the loads
+constexpr int PF_ROWS = 32;   // plane rows between the L2 prefetch front and the loads (ctx default; 16..32 measured equal to 2 % better)
 
 // Pull the source rows of plane rows [r0, r1) of the image at `base` into L2: one bulk prefetch per
 // 3 KB source row, no registers, no shared memory.

@@ -59,12 +59,12 @@ def main():
                               "frac": rate * bench.ALGO_BYTES_PER_IMAGE / 1e9 / hbm, "same_hashes": same[v]}
         print(v, res[f"variant{v}"], flush=True)
     ctx.set_option("pdq.variant", 0)
-    for rows in (8, 16, 24, 32):
+    for rows in (16, 32, 48, 64, 96, 16):
         ctx.set_option("pdq.prefetch_rows", rows)
         ms = run(pool, 1024, 768)
         res[f"prefetch_rows{rows}"] = {"ms": ms, "img_per_s": n / (ms * 1e-3)}
         print("pf rows", rows, ms, flush=True)
-    ctx.set_option("pdq.prefetch_rows", 16)
+    ctx.set_option("pdq.prefetch_rows", 32)
     # 512 x 512 (configs[3] shape): 3 x as many images in the same bytes
     sq = pool.reshape(-1)[: (n * 3) * 512 * 512 * 3].reshape(n * 3, 512, 512, 3)
     out_hash = torch.empty((n * 3, 32), dtype=torch.uint8, device="cuda")
