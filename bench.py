@@ -482,7 +482,7 @@ def main():
     if rank == 0:
         n_feed = 2048
         pageable = [np.array(host_np[k % Be]) for k in range(64)]      # 64 distinct pageable images, cycled
-        workers = max(2, min(16, (os.cpu_count() or 4) // max(1, world)))
+        workers = max(2, min(8, ((os.cpu_count() or 4) // 2) // max(1, world)))   # more copy threads than that fight the DMA reads
         fdr = scanner.Feeder()
         scanner.hash_files_batched(range(n_feed), decode=lambda k: pageable[k % 64], workers=workers, batch_size=256,
                                    want_coeffs=False, ctx=ctx, feeder=fdr)   # warm-up: page-locks the staging buffers
