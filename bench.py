@@ -155,9 +155,22 @@ def pin_to_gpu_numa_node(gpu_index: int) -> dict:
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:      # NVML prints an 8-digit domain, sysfs a 4-digit one
             bus = bus[4:]
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         info["pci"] = bus
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        except OSError:
+            node = -1
         if node < 0:
+            # no NUMA node in sysfs (virtualised topology): ask NVML which CPUs are closest to this GPU
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * wi + b for wi, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1}
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, allowed)
+                info.update(node="nvml-affinity", cpus=len(allowed))
+            else:
+                info["nvml_affinity_cpus"] = len(allowed)
             return info
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
