@@ -205,7 +205,9 @@ int rh_hamming_group_u64(rh_ctx *ctx, const uint64_t *hashes, const uint8_t *has
  * above that this returns a superset).  Output is CSR: group g holds
  * members[group_offsets[g] .. group_offsets[g+1]), seed first, then ascending.
  * members_cap / groups_cap are the capacities of the caller's arrays (n and n/2+1 always
- * suffice); *n_groups receives the number of groups.
+ * suffice); *n_groups receives the number of groups.  The adjacency is materialised on the host: inputs with
+ * more than 2^30 edges (e.g. a million identical hashes) return RH_EUNSUPPORTED -- rh_hamming_group never
+ * materialises edges and is the entry point for such libraries.
  */
 int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits, uint32_t max_dist,
                    uint32_t *members, size_t members_cap, uint32_t *group_offsets,

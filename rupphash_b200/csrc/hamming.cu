@@ -895,6 +895,10 @@ int rh_find_groups(rh_ctx *ctx, const uint8_t *hashes, int64_t n, int width_bits
                                     &count, edges.data(), cap);
         if (s != RH_OK) return s;
         if (count <= cap) break;
+        // the greedy star clustering needs the adjacency itself; inputs with O(n^2) edges (a library of
+        // identical files) are what the union-find entry points are for -- they never materialise edges
+        if (count > (uint64_t(1) << 30))
+            return fail(ctx, RH_EUNSUPPORTED, "rh_find_groups: more than 2^30 edges; use rh_hamming_group (connected components)");
         cap = (size_t)count;
     }
     // Host: CSR adjacency (both directions, ascending), then the sequential greedy star
