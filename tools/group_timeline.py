@@ -13,7 +13,7 @@ hashes, low_conf = planted_hashes(n, seed=0xB200, n_clusters=5000, identical_blo
 _, h = bench.pinned(torch, hashes)
 _, lc = bench.pinned(torch, low_conf)
 out = {}
-for name, nd, flags in (("1gpu", 1, 0), ("all_default", 0, 0), ("all_static", 0, 2), ("all_peercopy", 0, 1)):
+for name, nd, flags in (("1gpu", 1, 0), ("all_default_static_tiles", 0, 0), ("all_work_stealing", 0, 4), ("all_peercopy", 0, 1)):
     g = _lib.Group(n_dev=nd, flags=flags) if nd else _lib.Group(flags=flags)
     lab = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     rows = []
