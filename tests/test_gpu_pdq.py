@@ -294,7 +294,10 @@ def test_scanner_style_batching_feeder(ctx, orc):
 
 
 @pytest.mark.parametrize("shape,pad_row,pad_img", [((768, 1024, 3), 64, 4096), ((384, 512, 3), 16, 0),
-                                                   ((384, 512, 4), 48, 256), ((100, 449, 3), 5, 33)])
+                                                   ((384, 512, 4), 48, 256), ((100, 449, 3), 5, 33),
+                                                   # the float-chain kernel behind padded rows / images
+                                                   ((1024, 768, 3), 64, 4096), ((512, 384, 3), 32, 16), ((400, 320, 4), 16, 48),
+                                                   ((512, 384, 3), 7, 3)])   # unaligned pitches: generic pipeline
 @pytest.mark.parametrize("device_resident", [False, True])
 def test_row_and_image_pitches(ctx, orc, shape, pad_row, pad_img, device_resident):
     """rh_pdq_hash_batch with padded rows and padded images (the caller's pitches): the fused kernel's
