@@ -16,22 +16,24 @@
 //     decimated columns of pass 3, so only those are kept (64 floats per row).
 // The six inexact columns get the reference's real column chain (one lane each).
 //
-// Data flow.  pdq_edge_kernel first runs the six inexact columns of every image of the chunk
-// (one 128-thread CTA per image; it reads the first / last 48 source bytes of each row, ~4 % of the
-// pixels) and leaves their pass-2 values in a [n][H][6] scratch.  Then, per image (one CTA, 8 warps,
-// ~108 KB shared memory, 2 CTAs per SM, <= 128 registers so the row chains keep their state in
-// registers):
+// Data flow, per image (one CTA, 8 warps, 114 KB shared memory, 2 CTAs per SM, <= 128 registers so the
+// row chains keep their state in registers):
 //   for each band of 192 rows:
-//     F  8 warps : global (128-bit loads, three register sets in rotation, each pixel read once
-//                  + 4 % halo) -> luma -> 2x2 rounded average -> u8 luma band in shared memory
-//                  (the only copy of the plane)
+//     F  8 warps : global (128-bit evict-first loads, three register sets in rotation, an L2 prefetch
+//                  front through the bulk-copy engine; each pixel read ONCE: the rows two bands share
+//                  are carried over in shared memory) -> luma -> 2x2 rounded average -> u8 luma band in
+//                  shared memory (the only copy of the plane).  The two CTAs of an SM take turns here.
+//     E  the six inexact columns from the band's first / last eight luma bytes per row: pass-1
+//                  quotients (one thread per row), then the reference's column chain on six lanes,
+//                  in place, continued from band to band in registers
 //     C  8 warps : lane = row.  Horizontal 8-sums slide along the row in packed u16x2
 //                  registers, vertical window sums come from warp shuffles, S2d -> float ->
 //                  two-term-reciprocal division -> pass-3 chain; 64 samples per row go to a
-//                  per-CTA L2-resident scratch (column-major, coalesced)
-//   T  pass 4 over the scratch (64 column chains), decimate, then pdq_tail.cuh.
-// HBM traffic is the pixels (read once) plus 36 B of results; the f32 planes of the reference
-// never exist.
+//                  per-CTA L2-resident slab (column-major, coalesced, evict-last)
+//   P  pass 4 over the slab (pdq_pass4.cuh: chunks staged by cp.async.bulk + mbarrier, 64 column chains),
+//      decimate, then T: pdq_tail.cuh.
+// HBM traffic is the pixels (read once) plus 36 B of results: 1.03x algorithmic by ncu; the f32 planes
+// of the reference never exist.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -67,7 +69,7 @@ struct FusedArgs {
     int variant;       // A-B switches (rh_ctx_set_option "pdq.variant"), each bit turns one default OFF:
                        // 1 = pixels evict-first, 2 = slab evict-last, 4 = discard the slab's L2 lines after
                        // pass 4, 8 = the two CTAs of an SM alternate in the load phase
-    unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (RH_PDQ_PHASE_CLOCKS)
+    unsigned long long *phase_clk;   // nullptr, or [NPHASE] cycle totals of thread 0 of every CTA (ctx option "pdq.phase_clocks")
 };
 
 

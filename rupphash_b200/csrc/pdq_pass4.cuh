@@ -32,9 +32,9 @@ __device__ __forceinline__ void st_slab(float *p, float v, uint64_t pol) {
 
 // Pass 4: the column chains over the pass-3 samples (window WC, length H) for the 64 decimated
 // columns, keeping the 64 decimated rows (pdqhash.rs:435).  The slab is pulled from L2 into shared
-// memory P4_ROWS rows at a time with cp.async (16 bytes per request, no registers, every request of a
-// chunk in flight at once) into two buffers: chunk c + 1 lands while threads 0..63 (one per column)
-// walk chunk c at shared-memory latency, so only the first chunk's L2 round trip is exposed.
+// memory P4_ROWS rows at a time by the bulk-copy engine (one 512-byte cp.async.bulk per column, mbarrier
+// completion) into two buffers: chunk c + 1 lands while threads 0..63 (one per column) walk chunk c at
+// shared-memory latency, so only the first chunk's L2 round trip is exposed.
 // The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit accesses of the walk (8 lanes
 // per wavefront) are conflict-free.
 constexpr int P4_ROWS = 128;
@@ -43,14 +43,6 @@ static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitc
 static_assert((64 * (P4_ROWS / 4)) % FTHREADS == 0 && P4_ROWS % 8 == 0, "pass-4 staging has no remainder");
 constexpr size_t P4_STAGE_OFF = (sizeof(TailSmem) + 15) & ~size_t(15);   // 16-byte aligned for the 128-bit accesses
 constexpr size_t P4_SMEM_BYTES = P4_STAGE_OFF + 2 * 64 * P4_PITCH * 4;   // tail scratch + the two staging buffers
-
-__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct PhaseClock {
     unsigned long long *acc;
