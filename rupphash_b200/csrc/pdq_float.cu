@@ -22,7 +22,7 @@
 //   P3   one warp, lane = row of that band, while the other seven warps convert the next band: the row chain
 //        across the columns (eight per step from two conflict-free LDS.128, leaving values in registers),
 //        the running sums of the 64 decimated columns (pdqhash.rs:439) go to the per-CTA slab in L2 and are
-//        divided by their window sizes by the whole CTA before pass 4
+//        divided by their window sizes by the whole CTA inside pass 4 (in shared memory, as each chunk lands)
 //   then pass 4 over the slab and the 64x64 -> hash tail, both shared with pdq_fused.cu.
 #include "common.cuh"
 #include "pdq_pass4.cuh"
@@ -57,17 +57,6 @@ __host__ __device__ inline size_t float_smem_bytes(int W) {
     body = (body + 15) & ~size_t(15);
     if (body < P4_SMEM_BYTES) body = P4_SMEM_BYTES;   // the tail and pass-4 staging alias the band buffers
     return body + 16 * DCT_PITCH * 4;
-}
-
-// rows in the clipped window of output o of a line of `len` samples (pdqhash.rs:375, :383, :392)
-__device__ __forceinline__ int window_count(int o, int len, int ht, int hb) {
-    return min(o + hb, len - 1) - max(o - ht, 0) + 1;
-}
-
-// sum / count as the reference computes it (an IEEE f32 division); exact scaling for powers of two
-__device__ __forceinline__ float div_count(float sum, int cnt) {
-    if ((cnt & (cnt - 1)) == 0) return __fmul_rn(sum, 1.0f / (float)cnt);
-    return __fdiv_rn(sum, (float)cnt);
 }
 
 // Phase F for luma rows [i0, i1) of the plane: W / 8 threads per row, 8 plane pixels each, two register
@@ -192,7 +181,7 @@ __device__ __noinline__ void row_chain(float *q, int W) {
 }
 
 // the RAW running sums of the 64 decimated columns floor((2 j + 1) W / 128) (pdqhash.rs:439) of one row -> slab;
-// they are divided by their window sizes afterwards by the whole CTA (normalize_slab)
+// they are divided by their window sizes by pass 4, in shared memory, as each staged chunk lands (SlabNorm)
 __device__ __forceinline__ void row_samples(const float *q, int W, int hb, float *slab_row, uint64_t pol_slab) {
 #pragma unroll 8
     for (int j = 0; j < 64; j++) {
@@ -212,31 +201,6 @@ __device__ __forceinline__ void row_chain_any(int wr, float *q, int W, float *sl
         default: row_chain<8>(q, W); break;
     }
     row_samples(q, W, (wr + 2) / 2 - 1, slab_row, pol_slab);
-}
-
-// The decimated pass-3 sums of the whole image -> quotients (pdqhash.rs:375, :383, :392), in place in the slab:
-// every thread of the CTA takes part, the divisor depends on the column only.
-__device__ __forceinline__ void normalize_slab(float *p3t, int W, int H, int wr) {
-    const int half = (wr + 2) / 2, ht = wr - half, hb = half - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // one warp per decimated column (its divisor is a constant), lanes along the rows: coalesced, eight
-    // elements per lane and step with all loads issued before the first store
-    for (int j = warp; j < 64; j += FTHREADS / 32) {
-        const int cnt = window_count(((2 * j + 1) * W) >> 7, W, ht, hb);
-        const bool pow2 = (cnt & (cnt - 1)) == 0;
-        const float fc = (float)cnt, inv = 1.0f / fc;
-        float *col = p3t + (size_t)j * P3_PITCH;
-        for (int r0 = 0; r0 < H; r0 += 256) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(r0 + 32 * u + lane, H - 1));
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int r = r0 + 32 * u + lane;
-                if (r < H) __stcg(col + r, pow2 ? __fmul_rn(v[u], inv) : __fdiv_rn(v[u], fc));
-            }
-        }
-    }
 }
 
 template <int LAYOUT, bool DOWN2, int WC>
@@ -369,10 +333,9 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_float_kernel(const FloatArgs 
             __syncthreads();
             clk.lap(PH_P4_STAGE);   // warp 0 waiting for the front end (or vice versa)
         }
-        // the pass-3 sums -> quotients, then pass 4 + decimation into the tail's 64 x 64 buffer, quality / DCT / hash
-        normalize_slab(p3t, W, H, wr);
-        __syncthreads();
-        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, ts.p4_bar, clk);
+        // pass 4 (which first turns the slab's raw pass-3 sums into quotients, chunk by chunk in shared memory) +
+        // decimation into the tail's 64 x 64 buffer, then quality / DCT / hash
+        pass4<WC>(p3t, H, ts.B, reinterpret_cast<float *>(smem + P4_STAGE_OFF), ts.T, ts.p4_bar, clk, SlabNorm{W, wr});
         __syncthreads();
         {
             const int lines = (H * 4 + 127) / 128;

@@ -37,6 +37,24 @@ __device__ __forceinline__ void st_slab(float *p, float v, uint64_t pol) {
 // shared-memory latency, so only the first chunk's L2 round trip is exposed.
 // The pitch is a multiple of 4 floats with pitch / 4 odd: the 128-bit accesses of the walk (8 lanes
 // per wavefront) are conflict-free.
+// rows in the clipped window of output o of a line of `len` samples (pdqhash.rs:375, :383, :392)
+__device__ __forceinline__ int window_count(int o, int len, int ht, int hb) {
+    return min(o + hb, len - 1) - max(o - ht, 0) + 1;
+}
+
+// sum / count as the reference computes it (an IEEE f32 division); exact scaling for powers of two
+__device__ __forceinline__ float div_count(float sum, int cnt) {
+    if ((cnt & (cnt - 1)) == 0) return __fmul_rn(sum, 1.0f / (float)cnt);
+    return __fdiv_rn(sum, (float)cnt);
+}
+
+// How the slab reaches pass 4: already divided (pdq_fused.cu), or as the RAW pass-3 running sums of the
+// decimated columns of a plane W wide with row window wr (pdq_float.cu), which pass 4 divides by their window
+// sizes as each staged chunk lands -- in shared memory, by all 256 threads (thread = a quarter of a column).
+struct SlabNorm {
+    int W, wr;   // W == 0: the slab holds quotients already
+};
+
 constexpr int P4_ROWS = 128;
 constexpr int P4_PITCH = P4_ROWS + 4;
 static_assert((P4_PITCH / 4) % 2 == 1 && P4_PITCH % 4 == 0, "pass-4 staging pitch");
@@ -153,7 +171,7 @@ __device__ __forceinline__ void p4_issue(const float *p3t, int c0, float *stg, u
 
 template <int WC>
 __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *stage, float *shr, unsigned long long *bars,
-                                      PhaseClock &clk) {
+                                      PhaseClock &clk, const SlabNorm norm = SlabNorm{0, 0}) {
     constexpr int HALF = (WC + 2) / 2, HB = HALF - 1;
     const int j = threadIdx.x;
     float sum = 0.0f;
@@ -161,6 +179,13 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
 #pragma unroll
     for (int k = 0; k < 8; k++) prev[k] = 0.0f;
     uint64_t *bar = reinterpret_cast<uint64_t *>(bars);
+    // raw slab: this thread's column (thread = column j for the walk; column tid / 4 for the chunk pass) and divisor
+    int cnt_walk = 1, cnt_chunk = 1;
+    if (norm.W) {
+        const int half = (norm.wr + 2) / 2, ht = norm.wr - half, hb = half - 1;
+        cnt_walk = window_count(((2 * (j & 63) + 1) * norm.W) >> 7, norm.W, ht, hb);
+        cnt_chunk = window_count(((2 * (j >> 2) + 1) * norm.W) >> 7, norm.W, ht, hb);
+    }
     // the slab was written with ordinary stores by this CTA: order them before the copy engine's reads, and set up
     // the two stage barriers (64 arrivals: one per issuing thread) in memory the band buffers used until now
     fence_proxy_async_all();
@@ -182,10 +207,28 @@ __device__ __forceinline__ void pass4(const float *p3t, int H, float *B, float *
         float leave[HB > 0 ? HB : 1];
         if (last && j < 64) {
 #pragma unroll
-            for (int k = 0; k < HB; k++) leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
+            for (int k = 0; k < HB; k++) {
+                leave[k] = __ldcg(p3t + (size_t)j * P3_PITCH + (H - WC + k));
+                if (norm.W) leave[k] = div_count(leave[k], cnt_walk);
+            }
         }
         mbar_wait(&bar[buf], (parity >> buf) & 1u);   // this chunk has landed (the next one is still in flight)
         parity ^= 1u << buf;
+        if (norm.W) {   // raw sums -> quotients (pdqhash.rs:375, :383, :392), 32 consecutive rows of one column per thread
+            float *seg = stg + (j >> 2) * P4_PITCH + (j & 3) * (P4_ROWS / 4);
+            const bool pow2 = (cnt_chunk & (cnt_chunk - 1)) == 0;
+            const float fc = (float)cnt_chunk, inv = 1.0f / fc;
+#pragma unroll
+            for (int k = 0; k < P4_ROWS / 4; k += 4) {
+                float4 v = *reinterpret_cast<float4 *>(seg + k);
+                v.x = pow2 ? __fmul_rn(v.x, inv) : __fdiv_rn(v.x, fc);
+                v.y = pow2 ? __fmul_rn(v.y, inv) : __fdiv_rn(v.y, fc);
+                v.z = pow2 ? __fmul_rn(v.z, inv) : __fdiv_rn(v.z, fc);
+                v.w = pow2 ? __fmul_rn(v.w, inv) : __fdiv_rn(v.w, fc);
+                *reinterpret_cast<float4 *>(seg + k) = v;
+            }
+            __syncthreads();
+        }
         clk.lap(PH_P4_STAGE);
         if (j < 64) {
             p4_walk<WC>(stg + j * P4_PITCH, c0, rows, sum, prev);
