@@ -371,6 +371,7 @@ void box_precompute(int in_size, int out_size, BoxCoeffs *bc) {
 // one thread per output sample; `line_stride` / `tap_stride` walk the source along the filtered axis
 __global__ void box_resize_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n_img,
                                   int out_w, int out_h, size_t src_img, int src_row, int tap_stride, bool vertical,
+                                  int dst_row, size_t dst_img,
                                   const int *__restrict__ xmin, const int *__restrict__ cnt,
                                   const int16_t *__restrict__ k, int ksize, int precision) {
     const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -384,7 +385,7 @@ __global__ void box_resize_kernel(const uint8_t *__restrict__ src, uint8_t *__re
     int acc = 1 << (precision - 1);
     for (int t = 0; t < cnt[o]; t++) acc += (int)p[(size_t)t * tap_stride] * (int)kk[t];
     acc >>= precision;
-    dst[idx] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+    dst[img * dst_img + (size_t)y * dst_row + x] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
 }
 
 struct DeviceBox {
@@ -572,14 +573,16 @@ static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, i
     RH_TRY(ensure_dct(ctx, &d_dct));
     TailOut out{o_hash.dev, o_q.dev, o_c.dev, o_dih.dev};
     const bool on_device = is_device_ptr(pixels);
-    // host input is staged into 256-byte aligned buffers, so only the pitches matter there
+    // host input is staged into 256-byte aligned buffers, so only the pitches matter there; a Box-resized
+    // plane is written with its rows padded to 16 bytes (Wp), so it always qualifies
+    const size_t Wp = ((size_t)W + 15) & ~(size_t)15;
     const bool fused = pdq_fused_supported(W, H) != 0 && !ctx->pdq_force_generic &&
-                       (resize ? (((size_t)W * H) & 15) == 0
+                       (resize ? true
                                : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // every other plane up to 512 x 512 whose width is a multiple of 8 (portrait photos, small images): the
     // float-chain fused kernel; what remains (odd widths, tiny planes, unaligned rows) takes the generic pipeline
     const bool fused_float = !fused && pdq_float_supported(W, H) != 0 && !ctx->pdq_force_generic &&
-                             (resize ? (((size_t)W * H) & 15) == 0
+                             (resize ? true
                                      : pdq_fused_aligned(on_device ? (const void *)pixels : nullptr, row_pitch, img_pitch) != 0);
     // chunking: the generic pipeline keeps two f32 planes per image in scratch; host input is
     // streamed through two device buffers so the H2D copy of chunk k+1 overlaps the kernels of k.
@@ -635,7 +638,7 @@ static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, i
             uint8_t *Lfull = (uint8_t *)p;
             RH_TRY(scratch(ctx, S_W6, (size_t)cn * W * h, &p));
             uint8_t *Lh = (uint8_t *)p;
-            RH_TRY(scratch(ctx, S_W7, (size_t)cn * W * H, &p));
+            RH_TRY(scratch(ctx, S_W7, (size_t)cn * Wp * H, &p));
             uint8_t *Lr = (uint8_t *)p;
             if (layout == RH_LAYOUT_RGB8)
                 RH_TRY(launch_luma<RH_LAYOUT_RGB8>(ctx, false, d_px, row_pitch, img_pitch, (int)cn, w, h, Lfull));
@@ -644,17 +647,17 @@ static int pdq_hash_batch_impl(rh_ctx *ctx, const uint8_t *pixels, int layout, i
             else
                 RH_TRY(launch_luma<RH_LAYOUT_LUMA8>(ctx, false, d_px, row_pitch, img_pitch, (int)cn, w, h, Lfull));
             box_resize_kernel<<<cdiv((size_t)cn * W * h, 256), 256, 0, st>>>(Lfull, Lh, (size_t)cn, W, h, (size_t)w * h, w, 1,
-                                                                            false, bx.xmin, bx.cnt, bx.k, bx.ksize, bx.precision);
+                                                                            false, W, (size_t)W * h, bx.xmin, bx.cnt, bx.k, bx.ksize, bx.precision);
             RH_LAUNCHED(ctx, "box_resize_kernel");
             box_resize_kernel<<<cdiv((size_t)cn * W * H, 256), 256, 0, st>>>(Lh, Lr, (size_t)cn, W, H, (size_t)W * h, W, W,
-                                                                            true, by.xmin, by.cnt, by.k, by.ksize, by.precision);
+                                                                            true, (int)Wp, Wp * H, by.xmin, by.cnt, by.k, by.ksize, by.precision);
             RH_LAUNCHED(ctx, "box_resize_kernel");
             if (fused)
-                RH_TRY(pdq_fused_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+                RH_TRY(pdq_fused_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, Wp, Wp * H, out, off, d_dct));
             else if (fused_float)
-                RH_TRY(pdq_float_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+                RH_TRY(pdq_float_run(ctx, Lr, RH_LAYOUT_LUMA8, false, cn, W, H, Wp, Wp * H, out, off, d_dct));
             else
-                RH_TRY(generic_chunk(ctx, Lr, RH_LAYOUT_LUMA8, false, (int)cn, W, H, (size_t)W, (size_t)W * H, out, off, d_dct));
+                RH_TRY(generic_chunk(ctx, Lr, RH_LAYOUT_LUMA8, false, (int)cn, W, H, Wp, Wp * H, out, off, d_dct));
         } else if (fused)
             RH_TRY(pdq_fused_run(ctx, d_px, layout, down2, cn, W, H, row_pitch, img_pitch, out, off, d_dct));
         else if (fused_float)

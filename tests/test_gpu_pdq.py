@@ -150,7 +150,10 @@ def test_too_small_is_none(ctx):
 
 @pytest.mark.parametrize("shape", [(854, 1280, 3), (720, 1080, 3), (768, 780, 3), (1280, 854, 3), (513, 513),
                                    (1200, 900, 3), (2000, 1500), (700, 525, 4),
-                                   (600, 2000, 4), (1537, 640, 3), (5, 4000, 3)])
+                                   (600, 2000, 4), (1537, 640, 3), (5, 4000, 3),
+                                   # resized planes 504 and 136 columns wide (8 mod 16: the resized rows are padded to
+                                   # 16 bytes for the float-chain kernel; found by tools/fuzz_parity.py)
+                                   (1300, 1280, 3), (1500, 400)])
 def test_general_box_predownsample(ctx, orc, shape):
     """Sizes whose pre-downsample is not an exact 2x (pdqhash.rs:181-191 -> fast_image_resize Box
     convolution, restated by the oracle): fixed-point horizontal + vertical passes on the device."""
