@@ -7,7 +7,9 @@ sizes around every kernel's domain borders (landscape fused kernel, float-chain 
 pipeline, general Box pre-downsample), all three layouts, padded rows / images, image content
 from flat to pure noise, and for the grouping path random n, thresholds 0..63, variant counts,
 has_hash / low_conf masks and hash populations (uniform, planted clusters, shared prefixes, blocks
-of identical hashes).  Every case is compared bit for bit (hash, quality, coefficient bit
+of identical hashes); plus the smaller entry points: pHash, u64 grouping, star clustering
+(find_groups), hash / dihedral hashes from coefficients (ties, signed zeros, infinities,
+denormals), the scanner feeder with mixed sizes, group_max_dist.  Every case is compared bit for bit (hash, quality, coefficient bit
 patterns, dihedral hashes; labels, edge count, edge multiset).  A mismatch prints the case's
 parameters (they are all derived from --seed and the case number) and the run exits 1.
 RH_B200_LIB=rupphash_b200/librupphash_b200_dbg.so runs the same cases on the build with in-kernel
@@ -182,6 +184,185 @@ def hamming_case(ctx, rng, case):
     return ok, desc
 
 
+def phash_case(ctx, rng, case):
+    """rh_phash_batch (+ dihedral set) vs the oracle's restatement of phash.rs:48-83"""
+    from rupphash_b200 import phash
+    h = int([rng.integers(1, 40), rng.integers(20, 700), rng.integers(700, 1800), 32][int(rng.integers(0, 4))])
+    w = int([rng.integers(1, 40), rng.integers(20, 700), rng.integers(700, 1800), 32][int(rng.integers(0, 4))])
+    ch = [3, 4, 1][int(rng.integers(0, 3))]
+    n = int(rng.integers(1, 5))
+    imgs = make_images(rng, n, h, w, ch)
+    arr = imgs[..., 0] if ch == 1 else imgs
+    desc = dict(case=case, path="phash", h=h, w=w, ch=ch, n=n)
+    got, dih = phash.DctPhash(ctx).hash_batch(np.ascontiguousarray(arr), want_dihedral=True)
+    ok = True
+    for k in range(n):
+        want, _ = orc.phash_image(np.ascontiguousarray(arr[k]), layout={3: 0, 4: 1, 1: 2}[ch])
+        ok = ok and int(got[k]) == want and [int(x) for x in dih[k]] == orc.phash_dihedral(want)
+    return ok, desc
+
+
+def u64_case(ctx, rng, case):
+    """rh_hamming_group_u64 vs the 256-bit oracle on the zero-extended values (same distances)"""
+    import ctypes as C
+    n = int([rng.integers(1, 70), rng.integers(70, 5000)][int(rng.integers(0, 2))])
+    similarity = int(rng.integers(0, 33))
+    u = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    k = n // 3
+    if k:          # near copies of other values, both sides of the threshold
+        src = rng.integers(0, n, size=k)
+        dst = rng.integers(0, n, size=k)
+        for a, b in zip(src, dst):
+            bits = rng.choice(64, size=int(rng.integers(0, min(64, similarity + 6))), replace=False)
+            m = np.uint64(0)
+            for bpos in bits:
+                m |= np.uint64(1) << np.uint64(bpos)
+            u[b] = u[a] ^ m
+    has_hash = (rng.random(n) < 0.9).astype(np.uint8) if rng.integers(0, 3) == 0 else None
+    lc = (rng.random(n) < 0.2).astype(np.uint8) if rng.integers(0, 2) else None
+    variants = n_variants = None
+    if rng.integers(0, 2):
+        variants = rng.integers(0, 1 << 63, size=(n, 8), dtype=np.uint64)
+        variants[:, 0] = u
+        for a in rng.integers(0, n, size=max(1, n // 10)):
+            variants[a, int(rng.integers(1, 8))] = u[int(rng.integers(0, n))] ^ np.uint64(int(rng.integers(0, 8)))
+        if rng.integers(0, 2):
+            n_variants = rng.integers(0, 9, size=n).astype(np.uint8)
+    desc = dict(case=case, path="u64", n=n, similarity=similarity, variants=variants is not None,
+                n_variants=n_variants is not None, has_hash=has_hash is not None, low_conf=lc is not None)
+    wide = np.zeros((n, 32), np.uint8)
+    wide[:, :8] = u.view(np.uint8).reshape(n, 8)
+    wide_var = None
+    if variants is not None:
+        wide_var = np.zeros((n, 8, 32), np.uint8)
+        wide_var[:, :, :8] = np.ascontiguousarray(variants).view(np.uint8).reshape(n, 8, 8)
+    ref_labels, ref_cnt, _ = orc.group_generic(wide, similarity, has_hash=has_hash, variants=wide_var,
+                                               n_variants=n_variants, low_conf=lc, use_mih=False)
+    labels = np.empty(n, np.uint32)
+    cnt = C.c_uint64()
+    ctx.check(_lib.lib().rh_hamming_group_u64(ctx.handle, _lib.ptr(u), _lib.ptr(has_hash), _lib.ptr(variants),
+                                              _lib.ptr(n_variants), _lib.ptr(lc), n, similarity, _lib.ptr(labels),
+                                              C.byref(cnt)))
+    return cnt.value == ref_cnt and np.array_equal(labels, ref_labels), desc
+
+
+def find_groups_case(ctx, rng, case):
+    """rh_find_groups (greedy star clustering, hamminghash.rs:191-271) vs the oracle's MIH version, inside the
+    radius where the reference's probing is complete"""
+    from rupphash_b200 import hamminghash
+    n = int(rng.integers(2, 5000))
+    if rng.integers(0, 2):
+        max_dist = int(rng.integers(0, 32))
+        hashes, _, pop = make_hashes(rng, n, max_dist)
+        if pop in ("few_values", "dense_ball"):
+            hashes = hashes[:1500]
+    else:
+        max_dist = int(rng.integers(0, 16))
+        hashes = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+        k = n // 3
+        hashes[rng.integers(0, n, size=k)] = hashes[rng.integers(0, n, size=k)] ^ np.uint64(int(rng.integers(0, 1 << 10)))
+        pop = "u64"
+    desc = dict(case=case, path="find_groups", n=int(len(hashes)), max_dist=max_dist, population=pop)
+    got = hamminghash.find_groups(hamminghash.MIHIndex.new(hashes), max_dist, ctx)
+    want = orc.MIHIndex(hashes).find_groups(max_dist, threads=8)
+    return [g[0] for g in got] == [g[0] for g in want] and [sorted(g) for g in got] == [sorted(g) for g in want], desc
+
+
+def coeffs_case(ctx, rng, case):
+    """rh_pdq_hash_from_coeffs / rh_pdq_dihedral_from_coeffs / rh_pdq_from_buffer64 on awkward values"""
+    from rupphash_b200 import pdqhash
+    n = int(rng.integers(1, 200))
+    kind = int(rng.integers(0, 5))
+    coeffs = (rng.standard_normal((n, 256)) * float(10.0 ** rng.integers(-3, 6))).astype(np.float32)
+    if kind == 1:      # heavy ties around the median
+        coeffs = np.round(coeffs / np.float32(coeffs.std() + 1e-9) * 2).astype(np.float32)
+    elif kind == 2:    # signed zeros, infinities
+        m = rng.random((n, 256))
+        coeffs[m < 0.3] = 0.0
+        coeffs[(m >= 0.3) & (m < 0.5)] = -0.0
+        coeffs[m > 0.98] = np.inf
+        coeffs[(m > 0.96) & (m <= 0.98)] = -np.inf
+    elif kind == 3:    # denormals
+        coeffs = (coeffs * np.float32(1e-42)).astype(np.float32)
+    desc = dict(case=case, path="coeffs", n=n, kind=kind)
+    h = pdqhash.hash_from_coeffs(coeffs, ctx)
+    d = pdqhash.dihedral_from_coeffs(coeffs, ctx)
+    ok = all(np.array_equal(h[k], orc.to_hash(coeffs[k])) and np.array_equal(d[k], orc.dihedral(coeffs[k]))
+             for k in range(n))
+    m = int(rng.integers(1, 12))
+    bufs = (rng.random((m, 64, 64), dtype=np.float32) * np.float32(255.0)).astype(np.float32)
+    if rng.integers(0, 2):
+        bufs = np.round(bufs / 32).astype(np.float32) * 32
+    got = pdqhash.from_buffer64(bufs, want_coeffs=True, want_dihedral=True, ctx=ctx)
+    for k in range(m):
+        c = orc.dct64_to_16(bufs[k])
+        ok = (ok and np.array_equal(got["coeffs"][k].view(np.uint32), c.view(np.uint32).reshape(-1))
+              and np.float32(orc.quality(bufs[k])) == got["quality"][k] and np.array_equal(got["hash"][k], orc.to_hash(c))
+              and np.array_equal(got["dihedral"][k], orc.dihedral(c)))
+    return ok, desc
+
+
+def feeder_case(ctx, rng, case):
+    """scanner.hash_files_batched (pinned staging, async submits, mixed sizes in arrival order) vs the oracle"""
+    shapes = [pick_shape(rng) for _ in range(int(rng.integers(1, 4)))]
+    shapes = [(min(h, 1100), min(w, 1100)) for h, w in shapes]
+    ch = [3, 4, 1][int(rng.integers(0, 3))]
+    pools = [make_images(rng, int(rng.integers(1, 9)), h, w, ch) for h, w in shapes]
+    order = [(s, i) for s, pool in enumerate(pools) for i in range(len(pool))]
+    rng.shuffle(order)
+    imgs = [pools[s][i] if ch > 1 else pools[s][i][..., 0] for s, i in order]
+    batch = int(rng.integers(1, 9))
+    workers = int(rng.integers(0, 4))
+    desc = dict(case=case, path="feeder", shapes=shapes, ch=ch, images=len(imgs), batch_size=batch, workers=workers)
+    if workers:
+        res = scanner.hash_files_batched(list(range(len(imgs))), batch_size=batch, ctx=ctx, decode=lambda k: imgs[k],
+                                         workers=workers)
+    else:
+        res = scanner.hash_files_batched(iter(imgs), batch_size=batch, ctx=ctx)
+    wants = [orc.pdq_batch(pool, layout={3: 0, 4: 1, 1: 2}[ch], threads=8, want_coeffs=True) for pool in pools]
+    ok = len(res) == len(imgs)
+    for k, (s, i) in enumerate(order):
+        if not ok:
+            break
+        w = wants[s]
+        if not w["valid"][i]:
+            ok = res[k] is None
+        else:
+            ok = (res[k] is not None and np.array_equal(res[k]["hash"], w["hash"][i])
+                  and np.float32(res[k]["quality"]) == w["quality"][i] and np.array_equal(res[k]["coeffs"], w["coeffs"][i]))
+    return ok, desc
+
+
+def max_dist_case(ctx, rng, case):
+    """rh_group_max_dist vs the reference rule (scanner.rs:2217-2241)"""
+    n = int(rng.integers(8, 600))
+    hashes, _, _ = make_hashes(rng, n, 31)
+    n = len(hashes)
+    coeffs = (rng.standard_normal((n, 256)) * 30).astype(np.float32)
+    has_hash = (rng.random(n) > 0.1).astype(np.uint8)
+    has_hash[0] = 1
+    groups = []
+    for _ in range(int(rng.integers(1, 40))):
+        g = sorted(rng.choice(n, size=int(rng.integers(1, min(n, 12))), replace=False).tolist())
+        if any(has_hash[i] for i in g):
+            groups.append(g)
+    pivots = [next(i for i in g if has_hash[i]) for g in groups]
+    desc = dict(case=case, path="max_dist", n=n, groups=len(groups))
+    got = scanner.group_max_dist(groups, hashes, pivots, coefficients=coeffs, has_hash=has_hash, ctx=ctx)
+    got_plain = scanner.group_max_dist(groups, hashes, pivots, has_hash=has_hash, ctx=ctx)
+    ok = True
+    for g, members in enumerate(groups):
+        variants = orc.dihedral(coeffs[pivots[g]])
+        want = max(min(orc.hamming256(v, hashes[i]) for v in variants) for i in members if has_hash[i])
+        want_plain = max(orc.hamming256(hashes[pivots[g]], hashes[i]) for i in members if has_hash[i])
+        ok = ok and got[g] == want and got_plain[g] == want_plain
+    return ok, desc
+
+
+CASES = [pdq_case, pdq_case, hamming_case, pdq_case, phash_case, hamming_case, u64_case, pdq_case, find_groups_case,
+         coeffs_case, feeder_case, max_dist_case]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=240.0)
@@ -190,17 +371,17 @@ def main():
     args = ap.parse_args()
     ctx = _lib.Context(0)
     t0 = time.time()
-    counts = {"pdq": 0, "hamming": 0}
+    counts = {}
     failures = []
     case = 0
     while time.time() - t0 < args.seconds:
         rng = np.random.default_rng([args.seed, case])
-        fn = pdq_case if case % 3 != 2 else hamming_case
+        fn = CASES[case % len(CASES)]
         try:
             ok, desc = fn(ctx, rng, case)
         except Exception as e:       # an error return for a valid input is a failure too
-            ok, desc = False, {"case": case, "path": "pdq" if fn is pdq_case else "hamming", "error": str(e)[:300]}
-        counts[desc["path"]] += 1
+            ok, desc = False, {"case": case, "path": fn.__name__[:-5], "error": repr(e)[:300]}
+        counts[desc["path"]] = counts.get(desc["path"], 0) + 1
         if not ok:
             failures.append(desc)
             print("MISMATCH", json.dumps(desc), flush=True)
