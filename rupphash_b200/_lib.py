@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -207,12 +208,32 @@ class Context:
 GROUP_NO_NCCL, GROUP_STATIC_TILES, GROUP_STEAL_TILES = 1, 2, 4
 
 
+def _preload_bundled_nccl():
+    """The library dlopens libnccl.so.2 at rh_group_create.  A Python process that imports torch AFTER that
+    would find the (older) system copy already loaded under the same soname and fail to resolve torch's
+    symbols, so the pip-bundled NCCL that torch uses is loaded first when it exists (RH_NCCL_LIB overrides)."""
+    if os.environ.get("RH_NCCL_LIB") or "torch" in sys.modules:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 class Group:
     """rh_group: several GPUs of one box driven from this one process (in-library NCCL / NVLink peer
     access; no torch.distributed involved)."""
 
     def __init__(self, devices=None, n_dev: int = 0, flags: int = 0):
         self._h = _vp()
+        if not flags & GROUP_NO_NCCL:
+            _preload_bundled_nccl()
         if devices is not None:
             arr = (C.c_int * len(devices))(*[int(d) for d in devices])
             rc = lib().rh_group_create(arr, len(devices), int(flags), C.byref(self._h))

@@ -52,11 +52,13 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string *why) {
-        const char *names[] = {"libnccl.so.2", "libnccl.so"};
-        for (const char *nm : names) {
-            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-            if (handle) break;
-        }
+        // RH_NCCL_LIB names the copy to use; otherwise a libnccl.so.2 the process already holds (a host that
+        // also runs torch has torch's bundled one) is shared, and only then the loader's search path is used --
+        // two different NCCL builds behind one soname cannot live in one process
+        const char *names[] = {getenv("RH_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (names[0] && *names[0] && !handle) handle = dlopen(names[0], RTLD_NOW | RTLD_GLOBAL);
+        for (int k = 1; k < 3 && !handle; k++) handle = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
         if (!handle) {
             *why = std::string("dlopen libnccl.so.2: ") + dlerror();
             return false;

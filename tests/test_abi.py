@@ -121,3 +121,21 @@ def test_merge_groups_by_stem():
     assert scanner.merge_groups_by_stem([[7, 0], [8, 4]], paths) == [[0, 4, 7, 8]]
     assert scanner.merge_groups_by_stem([[3, 1, 1]], paths) == [[1, 3]]
     assert scanner.merge_groups_by_stem([], paths) == []
+
+
+def test_nccl_preload_keeps_torch_importable():
+    """The library dlopens libnccl.so.2 at rh_group_create; a Python process that imports torch afterwards must
+    still resolve torch's NCCL symbols (tools/fuzz_parity.py --multi found an ImportError when the older system
+    NCCL got loaded first), so `_lib.Group` loads the pip-bundled copy first."""
+    import subprocess
+    import sys
+    code = ("import sys\n"
+            "from rupphash_b200 import _lib\n"
+            "assert 'torch' not in sys.modules\n"
+            "_lib._preload_bundled_nccl()\n"
+            "import torch\n"
+            "import torch.distributed\n"
+            "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -1,6 +1,6 @@
 """Time-bounded randomised parity run of both hot paths through the C ABI against the CPU oracle.
 
-    python tools/fuzz_parity.py [--seconds 240] [--seed 1] [--out gpurun_out/fuzz.json]
+    python tools/fuzz_parity.py [--seconds 240] [--seed 1] [--out gpurun_out/fuzz.json] [--multi]
 
 The fixed cases live in tests/; this tool walks the input space the tests sample: random image
 sizes around every kernel's domain borders (landscape fused kernel, float-chain kernel, generic
@@ -359,6 +359,58 @@ def max_dist_case(ctx, rng, case):
     return ok, desc
 
 
+def multi_group_case(groups, rng, case):
+    """rh_hamming_group_multi over all GPUs of the box (one process) vs the oracle; the rh_group is one of
+    several created with different flags (NCCL / peer copies, static / stolen tiles)"""
+    import torch
+    flags, grp = groups[int(rng.integers(0, len(groups)))]
+    n = int([rng.integers(1, 70), rng.integers(70, 3000), rng.integers(3000, 12000)][int(rng.integers(0, 3))])
+    similarity = int([rng.integers(0, 32), rng.integers(32, 64), 63, 31, 40][int(rng.integers(0, 5))])
+    hashes, low_conf, pop = make_hashes(rng, n, similarity)
+    if pop in ("few_values", "dense_ball") and n > 4000:
+        n = 4000
+        hashes, low_conf = hashes[:n], low_conf[:n]
+    variants = random_variants(hashes, seed=int(rng.integers(1, 1 << 30))) if rng.integers(0, 2) else None
+    n_variants = rng.integers(0, 9, size=n).astype(np.uint8) if variants is not None and rng.integers(0, 2) else None
+    has_hash = (rng.random(n) < 0.9).astype(np.uint8) if rng.integers(0, 3) == 0 else None
+    lc = low_conf if rng.integers(0, 2) else None
+    on_device = bool(rng.integers(0, 2))
+    dev = int(rng.integers(0, grp.size))
+    desc = dict(case=case, path="multi_group", flags=flags, n=n, similarity=similarity, population=pop,
+                variants=variants is not None, n_variants=n_variants is not None, has_hash=has_hash is not None,
+                low_conf=lc is not None, device_resident=on_device, device=dev)
+    ref_labels, ref_cnt, _ = orc.group_generic(hashes, similarity, has_hash=has_hash, variants=variants,
+                                               n_variants=n_variants, low_conf=lc, use_mih=False)
+    put = (lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to("cuda:%d" % dev)) if on_device else (lambda a: a)
+    labels, cnt = scanner.group_labels_multi(grp, put(hashes), similarity, has_hash=put(has_hash), variants=put(variants),
+                                             n_variants=put(n_variants), low_conf=put(lc))
+    return cnt == ref_cnt and np.array_equal(labels, ref_labels), desc
+
+
+def multi_pdq_case(groups, rng, case):
+    """rh_pdq_hash_batch_multi: one batch split over the GPUs of the group vs the oracle"""
+    _, grp = groups[int(rng.integers(0, len(groups)))]
+    h, w = pick_shape(rng)
+    h, w = min(h, 1100), min(w, 1100)
+    ch = [3, 4, 1][int(rng.integers(0, 3))]
+    layout = {3: 0, 4: 1, 1: 2}[ch]
+    n = int(rng.integers(1, 24))
+    imgs = make_images(rng, n, h, w, ch)
+    desc = dict(case=case, path="multi_pdq", h=h, w=w, ch=ch, n=n)
+    want = orc.pdq_batch(imgs, layout=layout, threads=16, want_coeffs=True, want_dihedral=True)
+    got = {"hash": np.zeros((n, 32), np.uint8), "quality": np.zeros(n, np.float32),
+           "coeffs": np.zeros((n, 256), np.float32), "dihedral": np.zeros((n, 8, 32), np.uint8),
+           "valid": np.zeros(n, np.uint8)}
+    grp.check(_lib.lib().rh_pdq_hash_batch_multi(grp.handle, _lib.ptr(imgs), layout, n, w, h, 0, 0, _lib.ptr(got["hash"]),
+                                                 _lib.ptr(got["quality"]), _lib.ptr(got["coeffs"]),
+                                                 _lib.ptr(got["dihedral"]), _lib.ptr(got["valid"])))
+    ok = (np.array_equal(got["valid"], want["valid"]) and np.array_equal(got["hash"], want["hash"])
+          and np.array_equal(got["quality"].view(np.uint32), want["quality"].view(np.uint32))
+          and np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32))
+          and np.array_equal(got["dihedral"], want["dihedral"]))
+    return ok, desc
+
+
 CASES = [pdq_case, pdq_case, hamming_case, pdq_case, phash_case, hamming_case, u64_case, pdq_case, find_groups_case,
          coeffs_case, feeder_case, max_dist_case]
 
@@ -368,15 +420,22 @@ def main():
     ap.add_argument("--seconds", type=float, default=240.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default="")
+    ap.add_argument("--multi", action="store_true", help="the rh_group entry points over every GPU of the box")
     args = ap.parse_args()
-    ctx = _lib.Context(0)
+    cases = CASES
+    if args.multi:
+        ctx = [(f, _lib.Group(flags=f)) for f in (0, _lib.GROUP_NO_NCCL, _lib.GROUP_STEAL_TILES,
+                                                   _lib.GROUP_NO_NCCL | _lib.GROUP_STEAL_TILES)]
+        cases = [multi_group_case, multi_group_case, multi_pdq_case]
+    else:
+        ctx = _lib.Context(0)
     t0 = time.time()
     counts = {}
     failures = []
     case = 0
     while time.time() - t0 < args.seconds:
         rng = np.random.default_rng([args.seed, case])
-        fn = CASES[case % len(CASES)]
+        fn = cases[case % len(cases)]
         try:
             ok, desc = fn(ctx, rng, case)
         except Exception as e:       # an error return for a valid input is a failure too
@@ -390,11 +449,17 @@ def main():
         case += 1
     res = {"seed": args.seed, "seconds": round(time.time() - t0, 1), "cases": case, "by_path": counts,
            "failures": failures, "library": os.path.basename(_lib.SO_PATH)}
+    if args.multi:
+        res["gpus"] = ctx[0][1].size
     print(json.dumps(res))
     if args.out:
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)
-    ctx.close()
+    if args.multi:
+        for _, g in ctx:
+            g.close()
+    else:
+        ctx.close()
     sys.exit(1 if failures else 0)
 
 
