@@ -113,7 +113,9 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
     constexpr int SPP = DOWN2 ? 2 : 1;
     constexpr int BYTES = 8 * SPP * CH;  // source bytes per thread and source row
     constexpr int NW = BYTES / 4;
-    constexpr int SETS = NW * SPP * 3 <= 72 ? 3 : 2;
+    // as many sets as 72 registers of pixels hold, at most 8: without the 2x pre-downsample a set is only
+    // 24 bytes (RGB), and 3 sets left the phase waiting on latency (512 x 512: 777 cycles per 6 KB sweep)
+    constexpr int SETS = 72 / (NW * SPP) >= 8 ? 8 : (72 / (NW * SPP) >= 3 ? 72 / (NW * SPP) : 2);
     constexpr uint32_t ROWB = BYTES * 64;
     const size_t row_pitch = PACKED ? (size_t)ROWB : row_pitch_arg;
     const int col8 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
@@ -148,7 +150,8 @@ __device__ __forceinline__ void front_end(const uint8_t *__restrict__ src, size_
             if (q == 0 && pf_on) {
                 // PACKED rows are contiguous in memory: the 4 SETS plane rows of the sweep group pf_rows
                 // ahead are one byte range; lane 0 of each of the 8 warps prefetches an eighth of it
-                const int f0 = s - rsub + pf_rows, f1 = min(f0 + 4 * SETS, s_hi);
+                // (the front stays ahead of the loads, which run 4 (SETS - 1) rows ahead of the conversions)
+                const int f0 = s - rsub + max(pf_rows, 4 * (SETS - 1) + 16), f1 = min(f0 + 4 * SETS, s_hi);
                 constexpr uint32_t PIECE = (uint32_t)(4 * SETS * SPP) * ROWB / 8;
                 static_assert(PIECE % 16 == 0, "bulk prefetch granularity");
                 const int beg = ((Lr0 + f0) * SPP) * (int)ROWB + (int)(threadIdx.x >> 5) * (int)PIECE;
@@ -464,7 +467,10 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
                 }
                 __syncthreads();
             }
-            if (!(a.variant & 8)) {
+            // (only behind the 2x pre-downsample: a plane read 1:1 has a quarter of the pixels per plane row, its
+            // front end is a third of the time and taking turns costs 2.5 % there)
+            const bool take_turns = DOWN2 && !(a.variant & 8);
+            if (take_turns) {
                 // the two CTAs of an SM take turns in the load phase (front end ~ half of a CTA's time): one
                 // streams pixels while the other runs its chains, instead of both idling HBM or both queueing
                 // on it (+1.5-2 % measured, tools/pdq_variants.py)
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) pdq_fused_kernel(const FusedArgs 
             }
             front_end<LAYOUT, DOWN2, PACKED>(src, a.row_pitch, H, Lr0, nL, s_begin, sL, a.pf_mode, a.pf_rows, pol_px);
             __syncthreads();
-            if (!(a.variant & 8) && threadIdx.x == 0) atomicExch(&g_front_lock[smid], 0u);
+            if (take_turns && threadIdx.x == 0) atomicExch(&g_front_lock[smid], 0u);
             clk.lap(PH_FRONT);
             edge_inputs(sL, sE, max(s_begin, -Lr0), min(nL, H - Lr0));
             __syncthreads();

@@ -73,8 +73,15 @@ def main():
     rate = 3 * n / (ms * 1e-3)
     res["square512"] = {"ms": ms, "img_per_s": rate, "frac": rate * (512 * 512 * 3 + 36) / 1e9 / hbm}
     print("512x512", res["square512"], flush=True)
+    for v in (8, 0, 8, 0):     # the per-SM turn lock on a shape whose front end is a small share
+        ctx.set_option("pdq.variant", v)
+        ms = run(sq, 512, 512)
+        res.setdefault(f"square512_variant{v}", []).append({"ms": ms, "img_per_s": 3 * n / (ms * 1e-3)})
+        print("512x512 variant", v, ms, flush=True)
+    ctx.set_option("pdq.variant", 0)
     ctx.set_option("pdq.phase_clocks", 1)
     run(pool, 1024, 768, reps=3)
+    run(sq, 512, 512, reps=3)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "pdq_variants.json"), "w"), indent=1)
 
