@@ -59,7 +59,7 @@ int rh_ctx_destroy(rh_ctx *ctx);
 int rh_ctx_set_stream(rh_ctx *ctx, void *cuda_stream);
 int rh_ctx_sync(rh_ctx *ctx);
 /* Tuning knobs for benchmarks and A/B runs (never needed for correct results; the defaults are the
- * product path): "hamming.prefilter" (-1 = chosen by the threshold, 0 / 3 / 4 = pin the kernel variant),
+ * product path): "hamming.prefilter" (-1 = chosen on the device from the sampled selectivity, 0 / 3..7 = pin the kernel variant),
  * "pdq.force_generic", "pdq.prefetch", "pdq.prefetch_rows", "pdq.phase_clocks", "pdq.variant". */
 int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value);
 const char *rh_last_error(const rh_ctx *ctx);
@@ -69,6 +69,11 @@ uint64_t rh_kernel_launches(const rh_ctx *ctx);
 /* Device time of the most recent call's dominant kernel(s), measured with CUDA events on
  * the launching stream: [0] = ms, [1] = units processed (images or pairs). */
 int rh_last_kernel_time(const rh_ctx *ctx, double *ms, double *units);
+/* The tile-kernel variant the most recent rh_hamming_group / _shard / _edges call of this ctx chose on the device
+ * from its sampled selectivity (or the pinned one): 0 = full 256-bit distance for every pair (4 POPC), 3 / 4 = exact
+ * 96- / 128-bit prefix (2 / 3 POPC), 5 / 6 = OR lower bound over the first 160 / 192 bits (2 POPC), 7 = OR lower
+ * bound over all 256 bits (3 POPC); -1 before the first search.  Every variant gives identical results. */
+int rh_hamming_last_variant(const rh_ctx *ctx);
 
 /* pinned host staging the caller may use for the scanner-style batching pipeline */
 int rh_alloc_pinned(size_t bytes, void **out);

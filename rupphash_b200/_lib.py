@@ -24,7 +24,7 @@ PDQ_MIN_QUALITY = 50     # scanner.rs:1579
 # every symbol include/rupphash_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = [
     "rh_ctx_create", "rh_ctx_destroy", "rh_ctx_set_stream", "rh_ctx_sync", "rh_ctx_set_option", "rh_last_error", "rh_version",
-    "rh_kernel_launches", "rh_last_kernel_time", "rh_alloc_pinned", "rh_free_pinned",
+    "rh_kernel_launches", "rh_last_kernel_time", "rh_hamming_last_variant", "rh_alloc_pinned", "rh_free_pinned",
     "rh_pdq_hash_batch", "rh_pdq_hash_batch_async", "rh_ctx_wait", "rh_pdq_hash_from_coeffs", "rh_pdq_dihedral_from_coeffs", "rh_pdq_from_buffer64",
     "rh_phash_rotate_90", "rh_phash_rotate_180", "rh_phash_rotate_270", "rh_phash_flip_horizontal",
     "rh_phash_dihedral", "rh_phash_rotation_invariant", "rh_phash_batch",
@@ -78,6 +78,7 @@ def _declare(L):
     L.rh_kernel_launches.argtypes = [_vp]
     L.rh_kernel_launches.restype = C.c_uint64
     L.rh_last_kernel_time.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.rh_hamming_last_variant.argtypes = [_vp]
     L.rh_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(_vp)]
     L.rh_free_pinned.argtypes = [_vp]
     L.rh_pdq_hash_batch.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
@@ -198,6 +199,10 @@ class Context:
         ms, units = C.c_double(), C.c_double()
         lib().rh_last_kernel_time(self._h, C.byref(ms), C.byref(units))
         return ms.value, units.value
+
+    def hamming_last_variant(self) -> int:
+        """tile-kernel variant of the last search on this ctx (0, 3..7; -1 before the first)"""
+        return int(lib().rh_hamming_last_variant(self._h))
 
     def measure_peaks(self) -> dict:
         out = (C.c_double * 4)()

@@ -23,6 +23,7 @@ struct rh_ctx {
     std::string err;
     uint64_t launches = 0;
     double last_ms = 0.0, last_units = 0.0;
+    int last_hamming_variant = -1;   // rh_hamming_last_variant
     int sm_count = 148;
     // growable device scratch, one buffer per slot
     static constexpr int kSlots = 28;
@@ -35,7 +36,7 @@ struct rh_ctx {
     bool dct_ready = false;
     bool timing_pending = false;   // ev_a / ev_b bracket a kernel whose time has not been read yet
     // tuning knobs of rh_ctx_set_option (benchmarks / A-B runs); the defaults are the product path
-    int force_prefilter = -1;      // "hamming.prefilter": -1 = by threshold, 0 / 3 / 4 = pin the variant
+    int force_prefilter = -1;      // "hamming.prefilter": -1 = sampled selectivity, 0 / 3..7 = pin the variant
     int pdq_force_generic = 0;     // "pdq.force_generic"
     int pdq_prefetch = 2;          // "pdq.prefetch": L2 prefetch mode of the fused kernel's front end
     int pdq_prefetch_rows = 32;    // "pdq.prefetch_rows"

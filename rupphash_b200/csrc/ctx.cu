@@ -77,7 +77,8 @@ int rh_ctx_sync(rh_ctx *ctx) {
 int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return RH_EINVAL;
     if (!strcmp(key, "hamming.prefilter")) {
-        if (value != -1 && value != 0 && value != 3 && value != 4) return rh::fail(ctx, RH_EINVAL, "hamming.prefilter: -1, 0, 3 or 4");
+        if (value != -1 && value != 0 && (value < 3 || value > 7))
+            return rh::fail(ctx, RH_EINVAL, "hamming.prefilter: -1, 0 or 3..7");
         ctx->force_prefilter = value;
     } else if (!strcmp(key, "pdq.force_generic"))
         ctx->pdq_force_generic = value;
@@ -106,6 +107,8 @@ int rh_last_kernel_time(const rh_ctx *ctx, double *ms, double *units) {
     if (units) *units = ctx->last_units;
     return RH_OK;
 }
+
+int rh_hamming_last_variant(const rh_ctx *ctx) { return ctx ? ctx->last_hamming_variant : -1; }
 
 int rh_alloc_pinned(size_t bytes, void **out) {
     if (!out) return RH_EINVAL;

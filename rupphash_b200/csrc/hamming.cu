@@ -24,6 +24,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <new>
@@ -48,6 +49,7 @@ struct TileMeta {
     uint32_t nc, nq;      // dense candidates / query rows
     uint32_t n_qb, n_cb;  // query blocks of HT_TQ rows, candidate blocks of HT_TC
     uint32_t pass96, pass128;   // of PF_SAMPLES sampled (query, candidate) pairs: prefix distance <= threshold
+    uint32_t pass_or160, pass_or192, pass_or256;   // ... pairs whose OR lower bound over the first 160 / 192 / all 256 bits is <= threshold
 };
 
 // The prefix filter only pays when it rejects almost every pair: a warp refines a candidate as soon as
@@ -82,6 +84,29 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
+}
+// a | (b ^ c): one more word folded into an OR accumulator
+__device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// lower bound of the distance from the first 160 / 192 bits in two POPC: popc(x | y | z) <= popc(x) + popc(y) + popc(z),
+// so  popc(x0 | x1 | x2) + popc(x3 | x4 [| x5]) <= d(first 160 / 192 bits) <= d.  For unrelated hashes an OR of
+// three words has 28 +- 1.9 bits set, of two words 24 +- 2.4: the bound is ~N(52, 3.1^2) / ~N(56, 2.6^2), far more
+// selective than the exact 96-bit prefix (48 +- 4.9) or the exact 128-bit prefix (64 +- 5.7, 3 POPC) at the same
+// two POPC per pair; the 160-bit form needs 5 LOP3 like the 96-bit prefix, the 192-bit form 6.
+// WORDS = 7 stands for all 8 words in THREE groups (3 + 3 + 2 words, 3 POPC, ~N(80, 3.6^2)): selective up to the
+// largest threshold the reference accepts (63), where the exact kernel needs 4 POPC and 16 LOP3 per pair.
+template <int WORDS>
+__device__ __forceinline__ uint32_t or_bound(const uint32_t (&q)[8], const uint4 &a, const uint4 &b) {
+    const uint32_t o0 = or_xor(or_xor(q[0] ^ a.x, q[1], a.y), q[2], a.z);
+    uint32_t o1 = or_xor(q[3] ^ a.w, q[4], b.x);
+    if (WORDS >= 6) o1 = or_xor(o1, q[5], b.y);
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(__popc(o0)), "r"(__popc(o1)));   // the add on the FMA pipe
+    if (WORDS == 7) asm("mad.lo.u32 %0, %1, 1, %0;" : "+r"(d) : "r"(__popc(or_xor(q[6] ^ b.z, q[7], b.w))));
+    return d;
 }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
@@ -181,6 +206,10 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
             const uint4 b = sc[2 * c + 1];
 #pragma unroll
             for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+        } else if (PF >= 5) {
+            const uint4 b = sc[2 * c + 1];
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) d[r] = or_bound<PF>(q[r], a, b);
         } else {
 #pragma unroll
             for (int r = 0; r < HT_RQ; r++) {
@@ -199,7 +228,9 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
             for (int r = 0; r < HT_RQ; r++) {
                 if (d[r] > T) continue;
                 uint32_t full = d[r];
-                if (PF != 0) {
+                if (PF >= 5) {
+                    full = dist256(q[r], a, b);
+                } else if (PF != 0) {
                     if (PF == 3) full += __popc(q[r][3] ^ a.w);
                     full += __popc(q[r][4] ^ b.x) + __popc(q[r][5] ^ b.y) + __popc(q[r][6] ^ b.z) +
                             __popc(q[r][7] ^ b.w);
@@ -211,13 +242,20 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
     return local_edges;
 }
 
-// the variant every CTA of every GPU derives from the sampled selectivity (or the pinned one)
-__device__ __forceinline__ int choose_prefilter(const GroupArgs &g, const TileMeta &m) {
-    if (g.force_pf >= 0) return g.force_pf;
-    if (g.threshold > 63u) return 0;
+// the variant every CTA of every GPU derives from the sampled selectivity (or the pinned one); the host repeats
+// the choice from the same counters for rh_hamming_last_variant.  Two-POPC bounds first, the cheaper first.
+__host__ __device__ __forceinline__ int choose_variant(int force_pf, uint32_t threshold, const TileMeta &m) {
+    if (force_pf >= 0) return force_pf;
+    if (threshold > 63u) return 0;
+    if (m.pass_or160 <= PF_MAX_PASS) return 5;
     if (m.pass96 <= PF_MAX_PASS) return 3;
+    if (m.pass_or192 <= PF_MAX_PASS) return 6;
+    if (m.pass_or256 <= PF_MAX_PASS) return 7;
     if (m.pass128 <= PF_MAX_PASS) return 4;
     return 0;
+}
+__device__ __forceinline__ int choose_prefilter(const GroupArgs &g, const TileMeta &m) {
+    return choose_variant(g.force_pf, g.threshold, m);
 }
 
 // One instantiation per variant is launched for every search; the two that the sampled selectivity
@@ -370,6 +408,9 @@ __global__ void meta_kernel(const uint32_t *dpos, const uint32_t *qoff, uint32_t
     meta->n_cb = (nc + HT_TC - 1) / HT_TC;
     meta->pass96 = 0;
     meta->pass128 = 0;
+    meta->pass_or160 = 0;
+    meta->pass_or192 = 0;
+    meta->pass_or256 = 0;
     counters[0] = 0;   // comparison_count
     counters[1] = 0;   // edges written to the optional sink
     counters[2] = 0;   // next tile to claim (unused when the group's shared counter is given)
@@ -437,10 +478,21 @@ __global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, Ti
     const uint4 b = reinterpret_cast<const uint4 *>(cand)[(size_t)ci * 2];
     const uint32_t d96 = __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z);
     const uint32_t d128 = d96 + __popc(a.w ^ b.w);
+    const uint4 a2 = reinterpret_cast<const uint4 *>(qry)[(size_t)qi * 2 + 1];
+    const uint4 b2 = reinterpret_cast<const uint4 *>(cand)[(size_t)ci * 2 + 1];
+    const uint32_t o0 = __popc((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z));
+    const uint32_t dor5 = o0 + __popc((a.w ^ b.w) | (a2.x ^ b2.x));
+    const uint32_t dor = o0 + __popc((a.w ^ b.w) | (a2.x ^ b2.x) | (a2.y ^ b2.y));
     const uint32_t p96 = __syncthreads_count(d96 <= threshold), p128 = __syncthreads_count(d128 <= threshold);
+    const uint32_t dor7 = dor + __popc((a2.z ^ b2.z) | (a2.w ^ b2.w));
+    const uint32_t por = __syncthreads_count(dor <= threshold), por5 = __syncthreads_count(dor5 <= threshold);
+    const uint32_t por7 = __syncthreads_count(dor7 <= threshold);
     if (threadIdx.x == 0) {
         if (p96) atomicAdd(&meta->pass96, p96);
         if (p128) atomicAdd(&meta->pass128, p128);
+        if (por) atomicAdd(&meta->pass_or192, por);
+        if (por5) atomicAdd(&meta->pass_or160, por5);
+        if (por7) atomicAdd(&meta->pass_or256, por7);
     }
 }
 
@@ -657,6 +709,9 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr, int world) {
         // the variant is chosen on the device (choose_prefilter): the other two launches return at once
         const int f = pr.g.force_pf;
         if (f < 0 || f == 3) hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 5) hamming_tiles_kernel<5><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 6) hamming_tiles_kernel<6><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 7) hamming_tiles_kernel<7><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 4) hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 0) hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0) ctx->launches += 2;
@@ -732,11 +787,15 @@ int group_impl(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, cons
                            reinterpret_cast<uint2 *>(edg.dev), edg.dev ? edges_cap : 0, &d_counters));
     RH_TRY(lab.finish(ctx));
     RH_TRY(edg.finish(ctx));
-    u64 counts[2] = {0, 0};
-    RH_CUDA(ctx, cudaMemcpyAsync(counts, d_counters, 16, cudaMemcpyDeviceToHost, st));
+    u64 counts[16] = {0};   // [0] comparison count, [1] edges written, [8..] the TileMeta the kernels used
+    static_assert(sizeof(TileMeta) <= 64, "counters + meta share one 128-byte scratch block");
+    RH_CUDA(ctx, cudaMemcpyAsync(counts, d_counters, 128, cudaMemcpyDeviceToHost, st));
     RH_CUDA(ctx, cudaStreamSynchronize(st));   // the only host synchronisation of a search
     RH_TRY(finish_timing(ctx));
     if (out_edge_count) *out_edge_count = counts[0];
+    TileMeta hm;
+    memcpy(&hm, counts + 8, sizeof(hm));
+    ctx->last_hamming_variant = W == 8 ? choose_variant(ctx->force_prefilter, similarity, hm) : 0;
     return RH_OK;
 }
 

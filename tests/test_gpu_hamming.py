@@ -234,13 +234,17 @@ def test_prefilter_variants_agree(ctx, orc):
     hashes, low_conf = planted_hashes(n, seed=41)
     hashes[5000:5200, 12:] = hashes[100, 12:]     # pairs that pass the 96-bit prefix test but fail the full one
     hashes[6000:6100, :12] = hashes[200, :12]     # prefix-identical, full distance large
-    ref_labels, ref_cnt, _ = orc.group_generic(hashes, 31, low_conf=low_conf, threads=4)
+    hashes[7000:7100, :24] = hashes[300, :24]     # the first 192 bits identical (OR bound 0), the rest random
+    hashes[8000:8050, 24:] = hashes[400, 24:]     # only the last 64 bits shared
     try:
-        for pf in (0, 3, 4):
-            ctx.set_option("hamming.prefilter", pf)
-            labels, cnt = scanner.group_labels(hashes, 31, low_conf=low_conf, ctx=ctx)
-            assert cnt == ref_cnt, pf
-            assert np.array_equal(labels, ref_labels), pf
+        for sim in (31, 40, 63):
+            ref_labels, ref_cnt, _ = orc.group_generic(hashes, sim, low_conf=low_conf, threads=4, use_mih=(sim <= 31))
+            for pf in (0, 3, 4, 5, 6, 7):
+                ctx.set_option("hamming.prefilter", pf)
+                labels, cnt = scanner.group_labels(hashes, sim, low_conf=low_conf, ctx=ctx)
+                assert cnt == ref_cnt, (sim, pf)
+                assert np.array_equal(labels, ref_labels), (sim, pf)
+                assert ctx.hamming_last_variant() == pf
     finally:
         ctx.set_option("hamming.prefilter", -1)
 
@@ -260,6 +264,9 @@ def test_adaptive_variant_on_unselective_prefix(ctx, orc):
         ref_labels, ref_cnt, _ = orc.group_generic(hashes, 31, threads=4)
         labels, cnt = scanner.group_labels(hashes, 31, ctx=ctx)
         assert cnt == ref_cnt and np.array_equal(labels, ref_labels), shared
+        # the prefix bounds reject nothing here, the OR bound over all 256 bits (3 POPC) still does:
+        # 0 + 28 + 24 = 52 +- 3 bits (96 shared) / 0 + 24 + 24 = 48 +- 3.5 bits (128 shared) for unrelated pairs
+        assert ctx.hamming_last_variant() == 7, (shared, ctx.hamming_last_variant())
 
 
 def test_group_max_dist_matches_reference_rule(ctx, orc):
