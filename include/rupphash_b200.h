@@ -72,7 +72,8 @@ int rh_last_kernel_time(const rh_ctx *ctx, double *ms, double *units);
 /* The tile-kernel variant the most recent rh_hamming_group / _shard / _edges call of this ctx chose on the device
  * from its sampled selectivity (or the pinned one): 0 = full 256-bit distance for every pair (4 POPC), 3 / 4 = exact
  * 96- / 128-bit prefix (2 / 3 POPC), 5 / 6 = OR lower bound over the first 160 / 192 bits (2 POPC), 7 = OR lower
- * bound over all 256 bits (3 POPC); -1 before the first search.  Every variant gives identical results. */
+ * bound over all 256 bits (3 POPC); for rh_hamming_group_u64: 1 = one-POPC OR bound, 0 = exact distance for every
+ * pair; -1 before the first search.  Every variant gives identical results. */
 int rh_hamming_last_variant(const rh_ctx *ctx);
 
 /* pinned host staging the caller may use for the scanner-style batching pipeline */

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_u64_kernel(const Gro
         s_g.nc = m.nc;
     }
     const uint32_t T = g.threshold;
+    const bool use_bound = g.force_pf != 0 && m.pass_or160 <= PF_MAX_PASS;   // sampled like the 256-bit variants
     uint32_t local_edges = 0;
     for (;;) {
         __syncthreads();   // the previous tile's candidates and description are no longer needed
@@ -368,12 +369,34 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_u64_kernel(const Gro
             qf[r] = g.qfile[row];
         }
         __syncthreads();
-        for (int c = 0; c < cn; c++) {
-            const uint2 a = s_cand[c];
+        if (use_bound) {
+            // one POPC per pair: popc(x | y) <= popc(x) + popc(y) (24 +- 2.4 bits for unrelated values, thresholds
+            // are <= 15); the pairs it lets through get the exact distance
+            for (int c = 0; c < cn; c++) {
+                const uint2 a = s_cand[c];
+                uint32_t ob[HT_RQ];
 #pragma unroll
-            for (int r = 0; r < HT_RQ; r++) {
-                uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
-                if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+                for (int r = 0; r < HT_RQ; r++) ob[r] = __popc(or_xor(q[r].x ^ a.x, q[r].y, a.y));
+                uint32_t mn = ob[0];
+#pragma unroll
+                for (int r = 1; r < HT_RQ; r++) mn = min(mn, ob[r]);
+                if (mn <= T) {
+#pragma unroll
+                    for (int r = 0; r < HT_RQ; r++) {
+                        if (ob[r] > T) continue;
+                        const uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
+                        if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < cn; c++) {
+                const uint2 a = s_cand[c];
+#pragma unroll
+                for (int r = 0; r < HT_RQ; r++) {
+                    uint32_t d = __popc(q[r].x ^ a.x) + __popc(q[r].y ^ a.y);
+                    if (d <= T) local_edges += slow_hit(&s_g, d, qf[r], c0 + c);
+                }
             }
         }
     }
@@ -465,7 +488,9 @@ __global__ void pad_kernel(const TileMeta *meta, uint32_t *cand, uint32_t *qry, 
 }
 
 // prefix-filter selectivity on PF_SAMPLES pseudo-random (query row, candidate) pairs
-__global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, TileMeta *meta, uint32_t threshold) {
+// (a query row is never sampled against its own file: in a small input those pairs alone would exceed the limit)
+__global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, const uint32_t *qfile, TileMeta *meta,
+                                   uint32_t threshold) {
     const TileMeta m = *meta;
     if (m.nc == 0 || m.nq == 0) return;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,7 +498,9 @@ __global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, Ti
     x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
     uint32_t y = x * 0x27D4EB2Fu + 0x165667B1u;
     y ^= y >> 15; y *= 0x2C1B3C6Du; y ^= y >> 12;
-    const uint32_t qi = x % m.nq, ci = y % m.nc;
+    const uint32_t qi = x % m.nq;
+    uint32_t ci = y % m.nc;
+    if (ci == qfile[qi]) ci = (ci + 1u) % m.nc;
     const uint4 a = reinterpret_cast<const uint4 *>(qry)[(size_t)qi * 2];
     const uint4 b = reinterpret_cast<const uint4 *>(cand)[(size_t)ci * 2];
     const uint32_t d96 = __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z);
@@ -494,6 +521,24 @@ __global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, Ti
         if (por5) atomicAdd(&meta->pass_or160, por5);
         if (por7) atomicAdd(&meta->pass_or256, por7);
     }
+}
+
+__global__ void selectivity_u64_kernel(const uint32_t *cand, const uint32_t *qry, const uint32_t *qfile, TileMeta *meta,
+                                       uint32_t threshold) {
+    const TileMeta m = *meta;
+    if (m.nc == 0 || m.nq == 0) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x = t * 2654435761u + 0x9E3779B9u;
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    uint32_t y = x * 0x27D4EB2Fu + 0x165667B1u;
+    y ^= y >> 15; y *= 0x2C1B3C6Du; y ^= y >> 12;
+    const uint32_t qi = x % m.nq;
+    uint32_t ci = y % m.nc;
+    if (ci == qfile[qi]) ci = (ci + 1u) % m.nc;
+    const uint2 a = reinterpret_cast<const uint2 *>(qry)[qi];
+    const uint2 b = reinterpret_cast<const uint2 *>(cand)[ci];
+    const uint32_t p = __syncthreads_count(__popc((a.x ^ b.x) | (a.y ^ b.y)) <= threshold);
+    if (threadIdx.x == 0 && p) atomicAdd(&meta->pass_or160, p);
 }
 
 // number of candidate blocks that can hold a pair with j > i, per query block (entries from
@@ -652,8 +697,11 @@ int prepare(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, const u
     iota_kernel<<<cdiv(nc_pad, 256), 256, 0, st>>>(parent, (uint32_t)nc_pad);
     RH_LAUNCHED(ctx, "iota_kernel");
     if (W == 8) {
-        selectivity_kernel<<<PF_SAMPLES / 256, 256, 0, st>>>(cand, qry, meta, similarity);
+        selectivity_kernel<<<PF_SAMPLES / 256, 256, 0, st>>>(cand, qry, qfile, meta, similarity);
         RH_LAUNCHED(ctx, "selectivity_kernel");
+    } else {
+        selectivity_u64_kernel<<<PF_SAMPLES / 256, 256, 0, st>>>(cand, qry, qfile, meta, similarity);
+        RH_LAUNCHED(ctx, "selectivity_u64_kernel");
     }
     tile_counts_kernel<<<cdiv(n_qb_max + 1, 256), 256, 0, st>>>(qfile, meta, n_qb_max, tcount);
     RH_LAUNCHED(ctx, "tile_counts_kernel");
@@ -714,7 +762,7 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr, int world) {
         if (f < 0 || f == 7) hamming_tiles_kernel<7><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 4) hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 0) hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
-        if (f < 0) ctx->launches += 2;
+        if (f < 0) ctx->launches += 5;   // six instantiations launched, RH_LAUNCHED below counts one
     } else
         hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
     RH_LAUNCHED(ctx, "hamming_tiles_kernel");
@@ -795,7 +843,9 @@ int group_impl(rh_ctx *ctx, const uint8_t *hashes, const uint8_t *has_hash, cons
     if (out_edge_count) *out_edge_count = counts[0];
     TileMeta hm;
     memcpy(&hm, counts + 8, sizeof(hm));
-    ctx->last_hamming_variant = W == 8 ? choose_variant(ctx->force_prefilter, similarity, hm) : 0;
+    // (u64 hashes: 1 = the one-POPC OR bound, 0 = exact distance for every pair)
+    ctx->last_hamming_variant = W == 8 ? choose_variant(ctx->force_prefilter, similarity, hm)
+                                       : (ctx->force_prefilter != 0 && hm.pass_or160 <= PF_MAX_PASS ? 1 : 0);
     return RH_OK;
 }
 

@@ -208,6 +208,22 @@ def test_u64_group_and_find_groups_kats(ctx, orc):
                     par[max(a, b)] = min(a, b)
     assert cnt.value == want_cnt
     assert labels.tolist() == [find(i) for i in range(400)]
+    assert ctx.hamming_last_variant() == 1          # the one-POPC OR bound, chosen from the sampled selectivity
+    try:                                            # ... and the exact-distance loop gives the same
+        ctx.set_option("hamming.prefilter", 0)
+        labels2 = np.empty(400, np.uint32)
+        ctx.check(_lib.lib().rh_hamming_group_u64(ctx.handle, _lib.ptr(base), None, None, None, None, 400, 5,
+                                                  _lib.ptr(labels2), C.byref(cnt)))
+        assert cnt.value == want_cnt and np.array_equal(labels, labels2) and ctx.hamming_last_variant() == 0
+    finally:
+        ctx.set_option("hamming.prefilter", -1)
+    # values that share their low 40 bits: the bound rejects nothing, the kernel falls back to the exact loop
+    dense = (base & np.uint64(0xFFFFFF0000000000)) | np.uint64(0x123456789A)
+    ctx.check(_lib.lib().rh_hamming_group_u64(ctx.handle, _lib.ptr(dense), None, None, None, None, 400, 15,
+                                              _lib.ptr(labels2), C.byref(cnt)))
+    assert ctx.hamming_last_variant() == 0
+    d = np.array([[bin(int(a) ^ int(b)).count("1") for b in dense] for a in dense])
+    assert cnt.value == int(((d <= 15).sum() - 400) // 2)
 
 
 def test_find_groups_star_vs_oracle(ctx, orc):
