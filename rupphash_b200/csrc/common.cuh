@@ -33,6 +33,10 @@ struct rh_ctx {
     static constexpr int kHostSlots = 4;
     void *hslot_ptr[kHostSlots] = {};
     size_t hslot_bytes[kHostSlots] = {};
+    // buffers a growing slot left behind: queued work may still use them, so they are freed later, when the
+    // ctx is idle (rh::reap_retired) -- growing a slot never waits for the device
+    std::vector<void *> retired, retired_host;
+    size_t retired_bytes = 0;
     bool dct_ready = false;
     bool timing_pending = false;   // ev_a / ev_b bracket a kernel whose time has not been read yet
     // tuning knobs of rh_ctx_set_option (benchmarks / A-B runs); the defaults are the product path
@@ -89,16 +93,42 @@ inline int fail(rh_ctx *ctx, int code, const char *what, cudaError_t ce = cudaSu
         if (_e != cudaSuccess) return rh::fail((ctx), RH_ECUDA, "launch " name, _e); \
     } while (0)
 
+// Frees the buffers that growing slots left behind once nothing queued can still use them: `force` after the
+// caller has synchronised both streams, otherwise only if both streams are idle right now (cudaFree would wait
+// for the device otherwise).
+inline void reap_retired(rh_ctx *ctx, bool force) {
+    if (ctx->retired.empty() && ctx->retired_host.empty()) return;
+    if (!force) {
+        const bool idle = cudaStreamQuery(ctx->stream) == cudaSuccess && cudaStreamQuery(ctx->copy_stream) == cudaSuccess;
+        if (!idle) {
+            cudaGetLastError();   // cudaErrorNotReady is an answer, not a failure (launch errors are checked at the launch)
+            return;
+        }
+    }
+    for (void *p : ctx->retired) cudaFree(p);
+    for (void *p : ctx->retired_host) cudaFreeHost(p);
+    ctx->retired.clear();
+    ctx->retired_host.clear();
+    ctx->retired_bytes = 0;
+}
+
 inline int scratch(rh_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (ctx->slot_bytes[slot] < bytes) {
+        reap_retired(ctx, false);
         if (ctx->slot_ptr[slot]) {
-            // the buffer may still be in use by queued work
-            RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-            cudaFree(ctx->slot_ptr[slot]);
+            // the old buffer may still be in use by queued work: it is retired, not freed, so growing a slot does
+            // not wait for the device (round 1 synchronised both streams here); above 16 GiB of retired memory
+            // the wait is taken after all
+            ctx->retired.push_back(ctx->slot_ptr[slot]);
+            ctx->retired_bytes += ctx->slot_bytes[slot];
             ctx->slot_ptr[slot] = nullptr;
             ctx->slot_bytes[slot] = 0;
+            if (ctx->retired_bytes > (size_t(16) << 30)) {
+                RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+                reap_retired(ctx, true);
+            }
         }
         size_t want = bytes + bytes / 8;
         want = (want + 255) & ~size_t(255);
@@ -116,10 +146,9 @@ inline int scratch(rh_ctx *ctx, int slot, size_t bytes, void **out) {
 inline int host_scratch(rh_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (ctx->hslot_bytes[slot] < bytes) {
+        reap_retired(ctx, false);
         if (ctx->hslot_ptr[slot]) {
-            RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-            cudaFreeHost(ctx->hslot_ptr[slot]);
+            ctx->retired_host.push_back(ctx->hslot_ptr[slot]);
             ctx->hslot_ptr[slot] = nullptr;
             ctx->hslot_bytes[slot] = 0;
         }

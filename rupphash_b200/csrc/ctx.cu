@@ -41,6 +41,7 @@ int rh_ctx_destroy(rh_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    rh::reap_retired(ctx, true);
     for (int i = 0; i < rh_ctx::kSlots; i++)
         if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
     for (int i = 0; i < rh_ctx::kHostSlots; i++)
@@ -71,6 +72,8 @@ int rh_ctx_sync(rh_ctx *ctx) {
     if (!ctx) return RH_EINVAL;
     RH_CUDA(ctx, cudaSetDevice(ctx->device));
     RH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    rh::reap_retired(ctx, true);
     return RH_OK;
 }
 

@@ -344,3 +344,36 @@ def test_feeder_pipelined_with_pinned_staging(ctx, orc):
         assert np.array_equal(res[k]["hash"], w["hash"][i]) and res[k]["quality"] == w["quality"][i]
         assert np.array_equal(res[k]["coeffs"], w["coeffs"][i])
         assert np.array_equal(res2[k]["hash"], w["hash"][i]) and res2[k]["coeffs"] is None
+
+
+def test_async_batches_of_growing_size_on_a_fresh_ctx(orc):
+    """Every scratch slot of the ctx grows while earlier asynchronous batches are still queued: the buffers a
+    growing slot leaves behind are retired (freed once the ctx is idle), not freed under the queued work, and
+    growing does not wait for the device.  Results must be those of the synchronous path / the oracle."""
+    import ctypes as C
+    from rupphash_b200 import _lib
+    L = _lib.lib()
+    c = _lib.Context(0)
+    try:
+        sizes = [(3, 384, 512), (9, 768, 1024), (5, 1024, 768), (17, 768, 1024), (4, 1300, 1280), (33, 512, 384),
+                 (40, 768, 1024)]
+        jobs = []
+        for k, (n, h, w) in enumerate(sizes):
+            imgs = synth_images(n, h, w, seed=900 + k)
+            out = {"hash": np.zeros((n, 32), np.uint8), "quality": np.zeros(n, np.float32),
+                   "coeffs": np.zeros((n, 256), np.float32), "valid": np.zeros(n, np.uint8)}
+            t = C.c_uint64()
+            c.check(L.rh_pdq_hash_batch_async(c.handle, _lib.ptr(imgs), 0, n, w, h, 0, 0, _lib.ptr(out["hash"]),
+                                              _lib.ptr(out["quality"]), _lib.ptr(out["coeffs"]), None,
+                                              _lib.ptr(out["valid"]), C.byref(t)))
+            jobs.append((t.value, imgs, out))
+            if len(jobs) >= 3:                       # at most two batches in flight, like the feeder
+                tk, im, o = jobs.pop(0)
+                c.check(L.rh_ctx_wait(c.handle, tk))
+                check_exact(o, orc.pdq_batch(im, threads=8, want_coeffs=True))
+        for tk, im, o in jobs:
+            c.check(L.rh_ctx_wait(c.handle, tk))
+            check_exact(o, orc.pdq_batch(im, threads=8, want_coeffs=True))
+        c.check(L.rh_ctx_sync(c.handle))
+    finally:
+        c.close()
