@@ -139,7 +139,10 @@ uint64_t rh_phash_rotate_270(uint64_t h);
 uint64_t rh_phash_flip_horizontal(uint64_t h);
 void rh_phash_dihedral(uint64_t h, uint64_t out[8]);
 uint64_t rh_phash_rotation_invariant(uint64_t h);
-/* DctPhash::hash_image (phash.rs:48-83) over a batch; out_dihedral (n x 8) may be NULL. */
+/* DctPhash::hash_image (phash.rs:48-83) over a batch; out_dihedral (n x 8) may be NULL.
+ * PARITY UNVERIFIED against the real crates: the resize (image 0.25, Triangle), the Rec.709 luma and the DCT
+ * (rustdct) are not in the reference tree; this path is bit-exact with the oracle's restatement of them only
+ * (rustdct's butterfly summation order can differ in the last ulp, which can flip bits next to the median). */
 int rh_phash_batch(rh_ctx *ctx, const uint8_t *pixels, int layout, int64_t n, int w, int h,
                    size_t row_pitch, size_t img_pitch, uint64_t *out_hash, uint64_t *out_dihedral);
 
