@@ -36,9 +36,11 @@ HAMMING_N = 500_000                            # BASELINE.json configs[2]
 HAMMING_T = 31
 POPC_PER_PAIR = 8                              # algorithmic POPC.32 per 256-bit pair
 # POPC.32 the tile kernel executes per pair in its hot loop, by variant (hamming.cu)
-EXEC_POPC = {3: 2, 4: 3, 5: 2, 6: 2, 7: 3, 0: 4}
-EXEC_LOP3 = {3: 5, 4: 6, 5: 5, 6: 6, 7: 8, 0: 16}
+EXEC_POPC = {1: 1, 2: 1, 3: 2, 4: 3, 5: 2, 6: 2, 7: 3, 0: 4}
+EXEC_LOP3 = {1: 4, 2: 2, 3: 5, 4: 6, 5: 5, 6: 6, 7: 8, 0: 16}
 VARIANT_NAME = {0: "full 256-bit distance for every pair (16 LOP3 + 4 POPC, carry-save)",
+                1: "two-stage: OR lower bound over the first 128 bits (4 LOP3 + 1 POPC) + exact refine of survivors",
+                2: "two-stage: OR lower bound over the first 64 bits (2 LOP3 + 1 POPC) + exact refine of survivors",
                 3: "two-stage: exact 96-bit prefix distance (2 POPC) + exact refine of survivors",
                 4: "two-stage: exact 128-bit prefix distance (3 POPC) + exact refine of survivors",
                 5: "two-stage: OR lower bound over the first 160 bits (5 LOP3 + 2 POPC) + exact refine of survivors",

@@ -59,7 +59,7 @@ int rh_ctx_destroy(rh_ctx *ctx);
 int rh_ctx_set_stream(rh_ctx *ctx, void *cuda_stream);
 int rh_ctx_sync(rh_ctx *ctx);
 /* Tuning knobs for benchmarks and A/B runs (never needed for correct results; the defaults are the
- * product path): "hamming.prefilter" (-1 = chosen on the device from the sampled selectivity, 0 / 3..7 = pin the kernel variant),
+ * product path): "hamming.prefilter" (-1 = chosen on the device from the sampled selectivity, 0..7 = pin the kernel variant),
  * "pdq.force_generic", "pdq.prefetch", "pdq.prefetch_rows", "pdq.phase_clocks", "pdq.variant". */
 int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value);
 const char *rh_last_error(const rh_ctx *ctx);
@@ -71,7 +71,8 @@ uint64_t rh_kernel_launches(const rh_ctx *ctx);
 int rh_last_kernel_time(const rh_ctx *ctx, double *ms, double *units);
 /* The tile-kernel variant the most recent rh_hamming_group / _shard / _edges call of this ctx chose on the device
  * from its sampled selectivity (or the pinned one): 0 = full 256-bit distance for every pair (4 POPC), 3 / 4 = exact
- * 96- / 128-bit prefix (2 / 3 POPC), 5 / 6 = OR lower bound over the first 160 / 192 bits (2 POPC), 7 = OR lower
+ * 96- / 128-bit prefix (2 / 3 POPC), 2 / 1 = OR lower bound over the first 64 / 128 bits (1 POPC; strict thresholds),
+ * 5 / 6 = OR lower bound over the first 160 / 192 bits (2 POPC), 7 = OR lower
  * bound over all 256 bits (3 POPC); for rh_hamming_group_u64: 1 = one-POPC OR bound, 0 = exact distance for every
  * pair; -1 before the first search.  Every variant gives identical results. */
 int rh_hamming_last_variant(const rh_ctx *ctx);

@@ -80,8 +80,7 @@ int rh_ctx_sync(rh_ctx *ctx) {
 int rh_ctx_set_option(rh_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return RH_EINVAL;
     if (!strcmp(key, "hamming.prefilter")) {
-        if (value != -1 && value != 0 && (value < 3 || value > 7))
-            return rh::fail(ctx, RH_EINVAL, "hamming.prefilter: -1, 0 or 3..7");
+        if (value < -1 || value > 7) return rh::fail(ctx, RH_EINVAL, "hamming.prefilter: -1 or 0..7");
         ctx->force_prefilter = value;
     } else if (!strcmp(key, "pdq.force_generic"))
         ctx->pdq_force_generic = value;

@@ -50,6 +50,7 @@ struct TileMeta {
     uint32_t n_qb, n_cb;  // query blocks of HT_TQ rows, candidate blocks of HT_TC
     uint32_t pass96, pass128;   // of PF_SAMPLES sampled (query, candidate) pairs: prefix distance <= threshold
     uint32_t pass_or160, pass_or192, pass_or256;   // ... pairs whose OR lower bound over the first 160 / 192 / all 256 bits is <= threshold
+    uint32_t pass_or64, pass_or128;                // ... whose ONE-POPC bound popc(x0 | x1) / popc(x0 | .. | x3) is <= threshold
 };
 
 // The prefix filter only pays when it rejects almost every pair: a warp refines a candidate as soon as
@@ -59,6 +60,7 @@ struct TileMeta {
 // device and every CTA derives the same variant from the two counters.
 constexpr uint32_t PF_SAMPLES = 16384;
 constexpr uint32_t PF_MAX_PASS = PF_SAMPLES * 3 / 1000;   // 0.3 %
+constexpr uint32_t PF_MAX_PASS_1 = PF_SAMPLES / 2000;      // 0.05 % for the one-POPC bounds: a refinement costs more next to a cheaper hot loop
 
 struct GroupArgs {
     const uint32_t *cand;     // [nc_pad][W] dense candidate hashes, zero padded to HT_TC rows
@@ -96,10 +98,14 @@ __device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {
 // three words has 28 +- 1.9 bits set, of two words 24 +- 2.4: the bound is ~N(52, 3.1^2) / ~N(56, 2.6^2), far more
 // selective than the exact 96-bit prefix (48 +- 4.9) or the exact 128-bit prefix (64 +- 5.7, 3 POPC) at the same
 // two POPC per pair; the 160-bit form needs 5 LOP3 like the 96-bit prefix, the 192-bit form 6.
+// WORDS = 2 / 4: a single group, ONE POPC (24 +- 2.4 / 30 +- 1.4 bits for unrelated hashes): enough for strict
+// thresholds (<= ~12 / <= ~24), where the search then runs at up to twice the two-POPC rate.
 // WORDS = 7 stands for all 8 words in THREE groups (3 + 3 + 2 words, 3 POPC, ~N(80, 3.6^2)): selective up to the
 // largest threshold the reference accepts (63), where the exact kernel needs 4 POPC and 16 LOP3 per pair.
 template <int WORDS>
 __device__ __forceinline__ uint32_t or_bound(const uint32_t (&q)[8], const uint4 &a, const uint4 &b) {
+    if (WORDS == 2) return __popc(or_xor(q[0] ^ a.x, q[1], a.y));
+    if (WORDS == 4) return __popc(or_xor(or_xor(or_xor(q[0] ^ a.x, q[1], a.y), q[2], a.z), q[3], a.w));
     const uint32_t o0 = or_xor(or_xor(q[0] ^ a.x, q[1], a.y), q[2], a.z);
     uint32_t o1 = or_xor(q[3] ^ a.w, q[4], b.x);
     if (WORDS >= 6) o1 = or_xor(o1, q[5], b.y);
@@ -206,6 +212,9 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
             const uint4 b = sc[2 * c + 1];
 #pragma unroll
             for (int r = 0; r < HT_RQ; r++) d[r] = dist256(q[r], a, b);
+        } else if (PF == 1 || PF == 2) {   // one-POPC bounds over the first 128 / 64 bits (the second half is not read)
+#pragma unroll
+            for (int r = 0; r < HT_RQ; r++) d[r] = or_bound<PF == 1 ? 4 : 2>(q[r], a, a);
         } else if (PF >= 5) {
             const uint4 b = sc[2 * c + 1];
 #pragma unroll
@@ -228,7 +237,7 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
             for (int r = 0; r < HT_RQ; r++) {
                 if (d[r] > T) continue;
                 uint32_t full = d[r];
-                if (PF >= 5) {
+                if (PF >= 5 || PF == 1 || PF == 2) {
                     full = dist256(q[r], a, b);
                 } else if (PF != 0) {
                     if (PF == 3) full += __popc(q[r][3] ^ a.w);
@@ -247,6 +256,8 @@ __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_
 __host__ __device__ __forceinline__ int choose_variant(int force_pf, uint32_t threshold, const TileMeta &m) {
     if (force_pf >= 0) return force_pf;
     if (threshold > 63u) return 0;
+    if (m.pass_or64 <= PF_MAX_PASS_1) return 2;
+    if (m.pass_or128 <= PF_MAX_PASS_1) return 1;
     if (m.pass_or160 <= PF_MAX_PASS) return 5;
     if (m.pass96 <= PF_MAX_PASS) return 3;
     if (m.pass_or192 <= PF_MAX_PASS) return 6;
@@ -434,6 +445,8 @@ __global__ void meta_kernel(const uint32_t *dpos, const uint32_t *qoff, uint32_t
     meta->pass_or160 = 0;
     meta->pass_or192 = 0;
     meta->pass_or256 = 0;
+    meta->pass_or64 = 0;
+    meta->pass_or128 = 0;
     counters[0] = 0;   // comparison_count
     counters[1] = 0;   // edges written to the optional sink
     counters[2] = 0;   // next tile to claim (unused when the group's shared counter is given)
@@ -514,12 +527,16 @@ __global__ void selectivity_kernel(const uint32_t *cand, const uint32_t *qry, co
     const uint32_t dor7 = dor + __popc((a2.z ^ b2.z) | (a2.w ^ b2.w));
     const uint32_t por = __syncthreads_count(dor <= threshold), por5 = __syncthreads_count(dor5 <= threshold);
     const uint32_t por7 = __syncthreads_count(dor7 <= threshold);
+    const uint32_t por2 = __syncthreads_count(__popc((a.x ^ b.x) | (a.y ^ b.y)) <= threshold);
+    const uint32_t por4 = __syncthreads_count(__popc((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) <= threshold);
     if (threadIdx.x == 0) {
         if (p96) atomicAdd(&meta->pass96, p96);
         if (p128) atomicAdd(&meta->pass128, p128);
         if (por) atomicAdd(&meta->pass_or192, por);
         if (por5) atomicAdd(&meta->pass_or160, por5);
         if (por7) atomicAdd(&meta->pass_or256, por7);
+        if (por2) atomicAdd(&meta->pass_or64, por2);
+        if (por4) atomicAdd(&meta->pass_or128, por4);
     }
 }
 
@@ -757,12 +774,14 @@ int run_tiles(rh_ctx *ctx, const Prepared &pr, int world) {
         // the variant is chosen on the device (choose_prefilter): the other two launches return at once
         const int f = pr.g.force_pf;
         if (f < 0 || f == 3) hamming_tiles_kernel<3><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 2) hamming_tiles_kernel<2><<<grid, HT_THREADS, 0, st>>>(pr.g);
+        if (f < 0 || f == 1) hamming_tiles_kernel<1><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 5) hamming_tiles_kernel<5><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 6) hamming_tiles_kernel<6><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 7) hamming_tiles_kernel<7><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 4) hamming_tiles_kernel<4><<<grid, HT_THREADS, 0, st>>>(pr.g);
         if (f < 0 || f == 0) hamming_tiles_kernel<0><<<grid, HT_THREADS, 0, st>>>(pr.g);
-        if (f < 0) ctx->launches += 5;   // six instantiations launched, RH_LAUNCHED below counts one
+        if (f < 0) ctx->launches += 7;   // eight instantiations launched, RH_LAUNCHED below counts one
     } else
         hamming_tiles_u64_kernel<<<grid, HT_THREADS, 0, st>>>(pr.g);
     RH_LAUNCHED(ctx, "hamming_tiles_kernel");

@@ -57,7 +57,7 @@ def main():
         out[f"sim63_pf{pf}"] = {"tile_ms": k, "wall_ms": w, "pairs_per_s": pairs / (k * 1e-3),
                                 "executed_popc_frac": pairs / (k * 1e-3) * {0: 4, 7: 3}[pf] / pk["popc_per_s"]}
     ctx.set_option("hamming.prefilter", -1)
-    for sim in (31, 40, 48, 56, 63):
+    for sim in (0, 8, 12, 16, 20, 24, 28, 31, 40, 48, 56, 63):
         k, w = timed(lambda: scanner.group_labels(d_h, sim, low_conf=d_l, ctx=ctx), reps=2)
         out[f"auto_sim{sim}"] = {"tile_ms": k, "wall_ms": w, "pairs_per_s": pairs / (k * 1e-3), "variant": ctx.hamming_last_variant()}
     shards = []
