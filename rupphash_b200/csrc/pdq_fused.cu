@@ -409,7 +409,7 @@ __device__ __forceinline__ void chain_phase(const uint8_t *sL, const float *sE, 
     uint4 cur = *reinterpret_cast<const uint4 *>(rowp);
     uint4 nxt = *reinterpret_cast<const uint4 *>(rowp + 16);
     chain_group<WC, G_FIRST>(st, cur, 0, y8, y4, pe, cnt, p3col, store, pol_slab);
-#pragma unroll 1
+#pragma unroll 4
     for (int g = 1; g < 32; g++) {
         cur = nxt;
         nxt = *reinterpret_cast<const uint4 *>(rowp + 16 * g + 16);   // g = 31: the zero pad at column 512
