@@ -204,7 +204,7 @@ template <int PF>
 __device__ __forceinline__ uint32_t search_tile(const uint4 *sc, int cn, uint32_t c0, const uint32_t (&q)[HT_RQ][8],
                                                 const uint32_t (&qf)[HT_RQ], uint32_t T, const GroupArgs *s_g) {
     uint32_t local_edges = 0;
-#pragma unroll 2
+#pragma unroll (PF >= 1 && PF <= 3 ? 4 : 2)
     for (int c = 0; c < cn; c++) {
         const uint4 a = sc[2 * c];
         uint32_t d[HT_RQ];
