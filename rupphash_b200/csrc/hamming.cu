@@ -13,8 +13,12 @@
 // bulk-copy engine (cp.async.bulk + mbarrier) into one of two shared-memory stages while the
 // previous tile is being searched, and read with warp-broadcast LDS.128; every thread keeps HT_RQ
 // query rows in registers, so one candidate fetch feeds HT_RQ pairs.
-// A pair costs 8 XOR + a 4-step carry-save compression (8 LOP3) + 4 POPC instead of 8 POPC:
+// A full distance costs 8 XOR + a 4-step carry-save compression (8 LOP3) + 4 POPC instead of 8 POPC:
 // POPC issues at a quarter of the LOP3 rate, so trading POPCs for LOP3s balances the two pipes.
+// The hot loop rarely needs it: the search is two-stage, and the first stage is a LOWER BOUND of the
+// distance that costs one to three POPC (exact prefixes, or popc of an OR of several XOR words); only
+// pairs whose bound is within the threshold get the full distance.  Which bound is used is decided on
+// the device from a sampled selectivity (choose_variant); every choice gives identical results.
 // Pairs under the threshold are rare; they take a divergent slow path that applies the exact
 // edge rule (j > i, low-confidence => distance 0 only) and hooks the union-find.
 //
@@ -53,11 +57,11 @@ struct TileMeta {
     uint32_t pass_or64, pass_or128;                // ... whose ONE-POPC bound popc(x0 | x1) / popc(x0 | .. | x3) is <= threshold
 };
 
-// The prefix filter only pays when it rejects almost every pair: a warp refines a candidate as soon as
-// ONE of its 128 pairs survives, so at a survival rate of ~0.6 % the two-stage kernel already costs as
+// A first-stage bound only pays when it rejects almost every pair: a warp refines a candidate as soon as
+// ONE of its 128 pairs survives, so at a survival rate of ~0.6 % a two-stage kernel already costs as
 // much as the full-distance one (measured: bench.py worst_case).  The rate is a property of the input
-// (uniform hashes: 2.6e-4 at threshold 31; hashes sharing a 96-bit prefix: 1), so it is sampled on the
-// device and every CTA derives the same variant from the two counters.
+// (uniform hashes, exact 96-bit prefix: 2.6e-4 at threshold 31; hashes sharing that prefix: 1), so it is
+// sampled on the device for every bound and every CTA derives the same variant from the counters.
 constexpr uint32_t PF_SAMPLES = 16384;
 constexpr uint32_t PF_MAX_PASS = PF_SAMPLES * 3 / 1000;   // 0.3 %
 constexpr uint32_t PF_MAX_PASS_1 = PF_SAMPLES / 2000;      // 0.05 % for the one-POPC bounds: a refinement costs more next to a cheaper hot loop
@@ -269,8 +273,8 @@ __device__ __forceinline__ int choose_prefilter(const GroupArgs &g, const TileMe
     return choose_variant(g.force_pf, g.threshold, m);
 }
 
-// One instantiation per variant is launched for every search; the two that the sampled selectivity
-// did not choose return at once (a few microseconds), so the variant is picked without a host round
+// One instantiation per variant is launched for every search; the seven that the sampled selectivity
+// did not choose return at once (~4 us each), so the variant is picked without a host round
 // trip and each instantiation keeps its own lean register allocation.
 template <int PF>
 __global__ void __launch_bounds__(HT_THREADS, 4) hamming_tiles_kernel(const GroupArgs g) {
